@@ -1,0 +1,175 @@
+/*
+ * rag_b200.h -- C ABI of the B200-native exact dense-retrieval engine.
+ *
+ * This is the drop-in boundary for the vector-search hot path of
+ * akak0487521/Local-RAG-System.  The reference has no FFI of its own: its hot
+ * path is the `chromadb` Python API (chromadb==0.5.3, requirements.txt:6).
+ * Each entry point below names the reference call it serves; the Python
+ * binding a maintainer adds is in INTEGRATION.md (ctypes, as shipped in
+ * local-rag-system_b200/_native.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative RAG_E* code on failure;
+ *     rag_last_error() returns a thread-local message for the last failure.
+ *   - no exceptions, no torch types, no C++ types cross this boundary.
+ *   - the caller owns every host buffer; the engine owns all device memory.
+ *   - rows are dense int64 indices local to one store (= one GPU shard);
+ *     string ids, metadata and documents stay on the host side of the ABI.
+ *   - a "key" is the 64-bit sortable pair  (ordered(fp32 distance) << 32 | row)
+ *     used for candidate exchange between shards; smaller key = better hit,
+ *     RAG_EMPTY_KEY marks an unused slot.
+ *   - functions taking `stream` (a cudaStream_t passed as void*) are
+ *     asynchronous on that stream; `*_dev` pointers are device pointers on the
+ *     store's device.  All other functions take HOST pointers and are
+ *     synchronous.
+ *   - thread safety: any number of concurrent queries; upsert/delete/set_mask
+ *     are exclusive (internal reader/writer lock), matching how the reference
+ *     calls Chroma from FastAPI worker threads + BackgroundTasks
+ *     (api/routes/kb.py:102-103,115,149).
+ */
+#ifndef RAG_B200_H
+#define RAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAG_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RAG_API __attribute__((visibility("default")))
+#else
+#define RAG_API
+#endif
+
+/* element type the corpus is stored in */
+#define RAG_DTYPE_F32 0
+#define RAG_DTYPE_BF16 1
+
+/* distance space == Chroma collection metadata "hnsw:space"
+ *   l2     d = sum((a-b)^2)                (reference default, api/app.py:91)
+ *   cosine d = 1 - a.b/(|a||b|)            (rows L2-normalised on upsert)
+ *   ip     d = 1 - a.b                                                       */
+#define RAG_SPACE_L2 0
+#define RAG_SPACE_COSINE 1
+#define RAG_SPACE_IP 2
+
+#define RAG_OK 0
+#define RAG_EINVAL (-1)   /* bad argument                                   */
+#define RAG_ECUDA (-2)    /* CUDA runtime / driver error (message has it)   */
+#define RAG_ENOMEM (-3)   /* device or host allocation failed               */
+#define RAG_ENODEV (-4)   /* no usable sm_100 device                        */
+
+#define RAG_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define RAG_MAX_K 1024
+#define RAG_MAX_MASK_SLOTS 16
+
+typedef struct rag_store rag_store;
+
+RAG_API const char* rag_last_error(void);
+RAG_API int rag_abi_version(void);
+
+/* number of visible CUDA devices (0 if none / no driver); never fails */
+RAG_API int rag_device_count(void);
+
+/* -- lifetime ------------------------------------------------------------
+ * chromadb.PersistentClient(path).get_or_create_collection(name, metadata)
+ *   api/app.py:89-91, scripts/build_index.py:15-17                          */
+RAG_API int rag_store_create(int dim, int dtype, int space, int device,
+                     int64_t capacity_hint, rag_store** out);
+RAG_API int rag_store_destroy(rag_store* s);
+/* make room for at least `rows` rows without further reallocation */
+RAG_API int rag_store_reserve(rag_store* s, int64_t rows);
+
+/* -- writes ----------------------------------------------------------------
+ * Collection.add / Collection.upsert
+ *   api/app.py:221, scripts/build_index.py:92-96, scripts/bulk_import.py:66-70,
+ *   scripts/ingest_docs_to_chroma.py:31
+ * vectors: n x dim fp32, row-major.  rows[i] >= 0 overwrites that row in
+ * place (upsert of an existing id); rows == NULL or rows[i] == -1 appends
+ * (a free row left by a delete is reused first).  out_rows (may be NULL)
+ * receives the row each vector landed in.  Cosine stores: the row is
+ * L2-normalised by the upsert kernel.                                        */
+RAG_API int rag_store_upsert(rag_store* s, int64_t n, const float* vectors,
+                     const int64_t* rows, int64_t* out_rows);
+/* same, vectors already on the store's device (bulk load / synthetic data) */
+RAG_API int rag_store_upsert_dev(rag_store* s, int64_t n, const float* vectors_dev,
+                         const int64_t* rows, int64_t* out_rows);
+
+/* Collection.delete(ids=...) / delete(where=...) after the host resolved ids
+ * to rows -- api/app.py:269, 306, 311.  Deleting a dead row is a no-op.      */
+RAG_API int rag_store_delete(rag_store* s, int64_t n, const int64_t* rows);
+
+/* -- state -------------------------------------------------------------------
+ * Collection.count() -- api/routes/system.py:33.  O(1).                      */
+RAG_API int64_t rag_store_count(const rag_store* s);      /* live rows               */
+RAG_API int64_t rag_store_rows(const rag_store* s);       /* high-water mark         */
+RAG_API int64_t rag_store_capacity(const rag_store* s);
+RAG_API int rag_store_dim(const rag_store* s);
+RAG_API int rag_store_dtype(const rag_store* s);
+RAG_API int rag_store_space(const rag_store* s);
+RAG_API int rag_store_device(const rag_store* s);
+/* 1 if row is live, 0 if dead / out of range */
+RAG_API int rag_store_is_live(const rag_store* s, int64_t row);
+/* number of engine kernels launched by this store since creation */
+RAG_API int64_t rag_store_kernel_launches(const rag_store* s);
+
+/* read vectors back as fp32 (the stored values: normalised / bf16-rounded) --
+ * Collection.get(include=["embeddings"])                                     */
+RAG_API int rag_store_fetch(rag_store* s, int64_t n, const int64_t* rows, float* out);
+
+/* -- `where` filters -----------------------------------------------------------
+ * Collection.query(where=...) -- api/app.py:540-548.  The host compiles the
+ * predicate to a bitmap (bit r of word r/64, LSB first, 1 = row r passes) and
+ * parks it in one of RAG_MAX_MASK_SLOTS slots; queries name the slot.
+ * nbits may be smaller than the row count: missing rows do not pass.         */
+RAG_API int rag_store_set_mask(rag_store* s, int slot, const uint64_t* bits, int64_t nbits);
+RAG_API int rag_store_clear_mask(rag_store* s, int slot);
+
+/* -- search --------------------------------------------------------------------
+ * Collection.query(query_embeddings, n_results, where)
+ *   api/app.py:544-549, scripts/query_local.py:29-34
+ * queries: B x dim fp32.  mask_slot = -1 for no filter.  Output arrays are
+ * B x k; out_counts[b] = number of valid hits (min(k, live & passing rows)),
+ * hits ascending by (distance, row); unused tail = row -1, distance +inf.
+ * `flags`: 0 = choose the kernel regime automatically,
+ *          RAG_QUERY_FORCE_STREAM / RAG_QUERY_FORCE_TENSOR pin it (tests).   */
+#define RAG_QUERY_AUTO 0
+#define RAG_QUERY_FORCE_STREAM 1
+#define RAG_QUERY_FORCE_TENSOR 2
+RAG_API int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_slot,
+                    int flags, int64_t* out_rows, float* out_dists, int32_t* out_counts);
+
+/* Asynchronous shard-local search for the multi-GPU path: queries_dev and
+ * out_keys_dev (B x k keys, ascending, RAG_EMPTY_KEY padded) are device
+ * pointers; nothing is copied to the host.  `row_base` (this shard's first
+ * global row) is added to the row field of every emitted key, so keys from
+ * different shards merge by plain 64-bit comparison in exactly the order a
+ * single store would produce.  Global rows must stay below 2^32.             */
+RAG_API int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, int mask_slot,
+                        int flags, uint32_t row_base, uint64_t* out_keys_dev, void* stream);
+
+/* Cross-shard merge (after the NCCL all-gather of per-shard candidates):
+ * keys_dev is G x B x k (each list ascending).  Writes B x k global rows /
+ * distances and B counts on the device; any output pointer may be NULL.      */
+RAG_API int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* keys_dev,
+                       uint64_t* out_keys_dev, int64_t* out_rows_dev, float* out_dists_dev,
+                       int32_t* out_counts_dev, void* stream);
+
+/* helpers to (de)compose keys on the host */
+RAG_API uint64_t rag_key_pack(float dist, uint32_t row);
+RAG_API float rag_key_dist(uint64_t key);
+RAG_API uint32_t rag_key_row(uint64_t key);
+
+/* -- introspection for bench.py / profiles -------------------------------------
+ * Device-side duration (ms, CUDA events on the engine's stream) of the scan /
+ * contraction kernel of the most recent rag_store_query on this thread's
+ * store, and which regime it ran (1 = stream, 2 = tensor).                   */
+RAG_API int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAG_B200_H */

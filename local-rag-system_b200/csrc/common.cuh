@@ -1,0 +1,104 @@
+// Shared device/host helpers for the B200 dense-retrieval engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rag {
+
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kWarp = 32;
+
+// ---- sortable keys --------------------------------------------------------
+// key = (ordered(fp32 distance) << 32) | row.  `ordered` maps IEEE-754 floats
+// to unsigned ints with the same ordering, so "k smallest keys" is "k smallest
+// distances, ties broken by lower row" -- the oracle's order
+// (oracle/exact_search.py: topk_stable).
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float dist, uint32_t row) {
+  return (static_cast<uint64_t>(float_to_ordered(dist)) << 32) | row;
+}
+__host__ __device__ __forceinline__ float key_dist(uint64_t k) {
+  return ordered_to_float(static_cast<uint32_t>(k >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) {
+  return static_cast<uint32_t>(k & 0xFFFFFFFFull);
+}
+
+__host__ __device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+#ifdef __CUDACC__
+// ---- streaming 16-byte load: read-only path, do not allocate in L1 ---------
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// ---- warp-cooperative insertion into an ascending list in shared memory ----
+// L[0..k) sorted ascending (kEmptyKey padded).  Precondition: key < L[k-1].
+// All 32 lanes call with the same arguments.
+__device__ __forceinline__ void warp_list_insert(uint64_t* L, int k, uint64_t key, int lane) {
+  int pos = 0;
+  for (int base = 0; base < k; base += kWarp) {
+    int i = base + lane;
+    uint64_t e = (i < k) ? L[i] : kEmptyKey;
+    pos += __popc(__ballot_sync(0xffffffffu, e < key));
+  }
+  for (int base = ((k - 1) / kWarp) * kWarp; base >= 0; base -= kWarp) {
+    int i = base + lane;
+    bool mv = (i < k) && (i > pos);
+    uint64_t prev = mv ? L[i - 1] : 0;
+    __syncwarp();
+    if (mv) L[i] = prev;
+    __syncwarp();
+  }
+  if (lane == 0) L[pos] = key;
+  __syncwarp();
+}
+
+// ---- CTA-wide bitonic sort of n (power of two) keys in shared memory ---------
+__device__ __forceinline__ void block_bitonic_sort(uint64_t* a, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool up = ((lo & size) == 0);
+        uint64_t x = a[lo], y = a[hi];
+        if ((x > y) == up) { a[lo] = y; a[hi] = x; }
+      }
+    }
+  }
+  __syncthreads();
+}
+#endif  // __CUDACC__
+
+}  // namespace rag

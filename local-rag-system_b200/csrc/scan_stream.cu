@@ -1,0 +1,308 @@
+// K2 + K4: HBM-streaming exact scan with fused top-k.
+//
+// Replaces, for small query batches, what Chroma's BruteForceIndex.query /
+// hnswlib knn_query compute behind collection.query (reference call site
+// api/app.py:544-549): distances from every live, filter-passing corpus row to
+// each query, then the k smallest.  The B x N distance matrix never exists:
+// every warp keeps a running sorted top-k list per query in shared memory and
+// only rows beating the list's current k-th key are inserted.
+//
+// Roofline: HBM.  Algorithmic bytes per launch = live rows x row_bytes (+ one
+// bitmap word per 32 rows); every corpus byte is read exactly once per launch
+// (up to QB queries share the pass).
+//
+// Work decomposition
+//   grid.x = persistent CTAs (2 per SM), grid.y = query groups of QB
+//   one warp <- one block of 32 consecutive rows (= one word of the live and
+//   filter bitmaps), blocks interleaved over all warps of the grid.  Dead or
+//   filtered rows are skipped without touching their bytes (rows are whole
+//   128-byte lines for the dims that matter), so a selective `where` reads
+//   ~selectivity x corpus bytes.
+//   Within a block the warp takes R live rows at a time; every lane issues
+//   R x NJ independent 16-byte streaming loads (no L1 allocation) before the
+//   first FMA, so 16 resident warps/SM keep ~96 KB/SM in flight.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rag {
+namespace {
+
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+
+// ---- multi-value warp reduction ("transposed butterfly") -----------------------
+// Reduces V (power of two <= 32) per-lane partial sums across the warp with
+// V-1 + (5 - log2 V) shuffles instead of 5 V.  On return lane l holds the
+// warp total of value index  l >> (5 - log2 V).
+template <int C, int OFF>
+struct Fold {
+  template <int V>
+  static __device__ __forceinline__ float run(float (&v)[V], int lane) {
+    const bool upper = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < C / 2; ++i) {
+      float send = upper ? v[i] : v[i + C / 2];
+      float keep = upper ? v[i + C / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+    return Fold<C / 2, OFF / 2>::run(v, lane);
+  }
+};
+template <int OFF>
+struct Fold<1, OFF> {
+  template <int V>
+  static __device__ __forceinline__ float run(float (&v)[V], int) {
+    float x = v[0];
+#pragma unroll
+    for (int off = OFF; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    return x;
+  }
+};
+
+template <int V> struct Log2 { static constexpr int value = 1 + Log2<V / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
+// one 16-byte chunk of a row against the matching query elements
+template <bool BF16, bool L2>
+__device__ __forceinline__ float chunk_acc(float acc, const uint4& v, const float4& qa, const float4& qb) {
+  if constexpr (BF16) {
+    float x0 = bf_lo(v.x), x1 = bf_hi(v.x), x2 = bf_lo(v.y), x3 = bf_hi(v.y);
+    float x4 = bf_lo(v.z), x5 = bf_hi(v.z), x6 = bf_lo(v.w), x7 = bf_hi(v.w);
+    if constexpr (L2) {
+      x0 -= qa.x; x1 -= qa.y; x2 -= qa.z; x3 -= qa.w;
+      x4 -= qb.x; x5 -= qb.y; x6 -= qb.z; x7 -= qb.w;
+      acc = fmaf(x0, x0, acc); acc = fmaf(x1, x1, acc); acc = fmaf(x2, x2, acc); acc = fmaf(x3, x3, acc);
+      acc = fmaf(x4, x4, acc); acc = fmaf(x5, x5, acc); acc = fmaf(x6, x6, acc); acc = fmaf(x7, x7, acc);
+    } else {
+      acc = fmaf(x0, qa.x, acc); acc = fmaf(x1, qa.y, acc); acc = fmaf(x2, qa.z, acc); acc = fmaf(x3, qa.w, acc);
+      acc = fmaf(x4, qb.x, acc); acc = fmaf(x5, qb.y, acc); acc = fmaf(x6, qb.z, acc); acc = fmaf(x7, qb.w, acc);
+    }
+  } else {
+    float x0 = __uint_as_float(v.x), x1 = __uint_as_float(v.y), x2 = __uint_as_float(v.z), x3 = __uint_as_float(v.w);
+    if constexpr (L2) {
+      x0 -= qa.x; x1 -= qa.y; x2 -= qa.z; x3 -= qa.w;
+      acc = fmaf(x0, x0, acc); acc = fmaf(x1, x1, acc); acc = fmaf(x2, x2, acc); acc = fmaf(x3, x3, acc);
+    } else {
+      acc = fmaf(x0, qa.x, acc); acc = fmaf(x1, qa.y, acc); acc = fmaf(x2, qa.z, acc); acc = fmaf(x3, qa.w, acc);
+    }
+  }
+  return acc;
+}
+
+// T: float or __nv_bfloat16.  QB queries share one pass.  NJ > 0: row is exactly
+// NJ x 32 chunks (fully unrolled, no guards); NJ == 0: any row length.
+// R rows in flight per warp.
+template <bool BF16, int QB, int NJ, int R, bool L2>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const ScanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int V = R * QB;
+  static_assert(V <= 32, "R*QB must fit one warp");
+  constexpr int SHIFT = 5 - Log2<V>::value;
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int cpr = a.cpr;
+  const int row_elems = a.row_elems;
+  const int k = a.k;
+  const int kpad = next_pow2(k);
+  const int b0 = blockIdx.y * QB;
+
+  float* q_s = reinterpret_cast<float*>(smem_raw);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(QB) * row_elems * sizeof(float));
+
+  // ---- stage queries (fp32, chunk-major so that lanes read consecutive float4) ----
+  for (int idx = threadIdx.x; idx < QB * row_elems; idx += blockDim.x) {
+    int qb = idx / row_elems, e = idx - qb * row_elems;
+    int b = b0 + qb;
+    float val = (b < a.B) ? a.queries[static_cast<size_t>(b) * row_elems + e] : 0.0f;
+    int dst;
+    if constexpr (BF16) {
+      int c = e >> 3, w = e & 7;
+      dst = qb * row_elems + (w >> 2) * (cpr * 4) + c * 4 + (w & 3);
+    } else {
+      dst = qb * row_elems + e;
+    }
+    q_s[dst] = val;
+  }
+  for (int idx = threadIdx.x; idx < QB * kScanWarps * kpad; idx += blockDim.x) lists[idx] = kEmptyKey;
+  __syncthreads();
+
+  // lane's value index after the multi-reduce, fixed for the whole kernel
+  const int my_idx = lane >> SHIFT;
+  const int my_i = my_idx / QB;
+  const int my_qb = my_idx - my_i * QB;
+  const bool rep = (lane & ((1 << SHIFT) - 1)) == 0;
+  uint64_t my_tau = kEmptyKey;   // current k-th best key of (this warp, my_qb)
+
+  const uint4* vec = reinterpret_cast<const uint4*>(a.vectors);
+  const int64_t nblk = (a.n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int64_t wstride = static_cast<int64_t>(gridDim.x) * kScanWarps;
+
+  for (int64_t blk = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; blk < nblk; blk += wstride) {
+    uint32_t m = __ldg(a.live + blk);
+    if (a.filter != nullptr) m &= (blk < a.filter_words) ? __ldg(a.filter + blk) : 0u;
+    const uint4* bbase = vec + static_cast<size_t>(blk) * kRowsPerBlock * cpr;
+    while (m) {
+      int r[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        r[i] = m ? (__ffs(m) - 1) : -1;
+        m &= (m - 1);
+      }
+      float acc[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] = 0.0f;
+
+      if constexpr (NJ > 0) {
+        uint4 v[R][NJ];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            v[i][j] = (r[i] >= 0) ? ldg_stream(bbase + static_cast<size_t>(r[i]) * cpr + j * 32 + lane)
+                                  : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int c = j * 32 + lane;
+#pragma unroll
+          for (int qb = 0; qb < QB; ++qb) {
+            const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
+            float4 qa = qrow[c];
+            float4 qh = BF16 ? qrow[cpr + c] : qa;
+#pragma unroll
+            for (int i = 0; i < R; ++i) acc[i * QB + qb] = chunk_acc<BF16, L2>(acc[i * QB + qb], v[i][j], qa, qh);
+          }
+        }
+      } else {
+        for (int c = lane; c < cpr; c += 32) {
+          uint4 v[R];
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+            v[i] = (r[i] >= 0) ? ldg_stream(bbase + static_cast<size_t>(r[i]) * cpr + c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int qb = 0; qb < QB; ++qb) {
+            const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
+            float4 qa = qrow[c];
+            float4 qh = BF16 ? qrow[cpr + c] : qa;
+#pragma unroll
+            for (int i = 0; i < R; ++i) acc[i * QB + qb] = chunk_acc<BF16, L2>(acc[i * QB + qb], v[i], qa, qh);
+          }
+        }
+      }
+
+      const float total = Fold<V, 16>::run(acc, lane);
+      int myr = r[0];
+#pragma unroll
+      for (int i = 1; i < R; ++i) myr = (my_i == i) ? r[i] : myr;
+      const float dist = L2 ? total : (1.0f - total);
+      const uint64_t key = make_key(dist, static_cast<uint32_t>(blk * kRowsPerBlock + myr));
+      uint32_t bal = __ballot_sync(0xffffffffu, rep && (myr >= 0) && (key < my_tau));
+      while (bal) {
+        const int src = __ffs(bal) - 1;
+        bal &= (bal - 1);
+        const uint64_t ck = shfl_u64(key, src);
+        const int sidx = src >> SHIFT;
+        const int cqb = sidx - (sidx / QB) * QB;
+        uint64_t* L = lists + (static_cast<size_t>(cqb) * kScanWarps + warp) * kpad;
+        if (ck < L[k - 1]) {   // tau may have tightened since the ballot
+          warp_list_insert(L, k, ck, lane);
+          if (my_qb == cqb) my_tau = L[k - 1];
+        }
+      }
+    }
+  }
+
+  // ---- CTA merge: sort each query's 8 warp lists together, emit the first k -------
+  __syncthreads();
+#pragma unroll 1
+  for (int qb = 0; qb < QB; ++qb) {
+    const int b = b0 + qb;
+    if (b >= a.B) break;
+    uint64_t* region = lists + static_cast<size_t>(qb) * kScanWarps * kpad;
+    block_bitonic_sort(region, kScanWarps * kpad);
+    uint64_t* out = a.partial + (static_cast<size_t>(blockIdx.x) * a.B + b) * k;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) out[j] = region[j];
+  }
+}
+
+size_t scan_smem_bytes(int QB, int row_elems, int k) {
+  return static_cast<size_t>(QB) * row_elems * sizeof(float) +
+         static_cast<size_t>(QB) * kScanWarps * next_pow2(k) * sizeof(uint64_t);
+}
+
+template <bool BF16, int QB, int NJ, int R>
+cudaError_t launch_one(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  if (a.l2) {
+    auto kern = scan_stream_kernel<BF16, QB, NJ, R, true>;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, kScanThreads, smem, st>>>(a);
+  } else {
+    auto kern = scan_stream_kernel<BF16, QB, NJ, R, false>;
+    if (smem > 48 * 1024) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, kScanThreads, smem, st>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+template <bool BF16, int QB>
+cudaError_t launch_qb(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  // rows in flight per warp chosen so that R*NJ ~ 12 independent 16-byte loads per lane
+  constexpr int R4 = (QB <= 8) ? 4 : 2;
+  if (a.cpr == 96) return launch_one<BF16, QB, 3, R4>(a, grid, smem, st);    // 768-d bf16, 384-d fp32
+  if (a.cpr == 192) return launch_one<BF16, QB, 6, 2>(a, grid, smem, st);    // 1536-d bf16, 768-d fp32
+  if (a.cpr == 64) return launch_one<BF16, QB, 2, R4>(a, grid, smem, st);    // 512-d bf16, 256-d fp32
+  if (a.cpr == 128) return launch_one<BF16, QB, 4, 2>(a, grid, smem, st);    // 1024-d bf16, 512-d fp32
+  return launch_one<BF16, QB, 0, R4>(a, grid, smem, st);
+}
+
+}  // namespace
+
+int scan_stream_grid_x(int sm_count, int64_t n_rows) {
+  int64_t nblk = (n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  int64_t want = (nblk + kScanWarps - 1) / kScanWarps;   // CTAs that would each get >= 1 block per warp
+  int64_t g = 2LL * sm_count;                              // 2 resident CTAs per SM, persistent
+  if (want < g) g = want;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+int scan_stream_max_qb(int dtype, int row_elems, int k) {
+  // shared memory per CTA must allow 2 CTAs/SM: keep it under ~100 KB
+  const size_t budget = 100 * 1024;
+  int qb = 8;
+  while (qb > 1 && scan_smem_bytes(qb, row_elems, k) > budget) qb >>= 1;
+  (void)dtype;
+  return qb;
+}
+
+cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st, int* launches) {
+  if (a.B <= 0 || a.k <= 0) return cudaErrorInvalidValue;
+  const int max_qb = scan_stream_max_qb(a.dtype, a.row_elems, a.k);
+  int QB = 1;
+  while (QB < a.B && QB < max_qb) QB <<= 1;
+  if (scan_smem_bytes(QB, a.row_elems, a.k) > 200 * 1024) return cudaErrorInvalidValue;
+  dim3 grid(a.grid_x, (a.B + QB - 1) / QB, 1);
+  const size_t smem = scan_smem_bytes(QB, a.row_elems, a.k);
+  const bool bf16 = (a.dtype == 1);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (QB) {
+    case 1: e = bf16 ? launch_qb<true, 1>(a, grid, smem, st) : launch_qb<false, 1>(a, grid, smem, st); break;
+    case 2: e = bf16 ? launch_qb<true, 2>(a, grid, smem, st) : launch_qb<false, 2>(a, grid, smem, st); break;
+    case 4: e = bf16 ? launch_qb<true, 4>(a, grid, smem, st) : launch_qb<false, 4>(a, grid, smem, st); break;
+    case 8: e = bf16 ? launch_qb<true, 8>(a, grid, smem, st) : launch_qb<false, 8>(a, grid, smem, st); break;
+    default: break;
+  }
+  if (launches) *launches += 1;
+  return e;
+}
+
+}  // namespace rag

@@ -1,0 +1,39 @@
+// Interface of the tensor-core (tcgen05) search regime used for large query batches.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace rag {
+namespace tensor {
+
+// batches larger than this go to the tensor regime when it supports the store
+constexpr int kStreamMaxBatch = 8;
+
+struct Plan;   // cached TMA descriptors etc. for one store
+
+struct Problem {
+  const void* vectors;      // [n_rows][row_elems] bf16, row-major
+  const float* norms2;      // [n_rows] |x|^2 of the stored rows (l2 space)
+  int64_t n_rows;
+  int row_elems, dim, dtype, space;
+  const uint32_t* live;
+  const uint32_t* filter;
+  int64_t filter_words;
+  const float* queries_raw; // [B][dim] fp32, unprepared
+  int B, k;
+  unsigned char* scratch;   // scratch_bytes() bytes
+  int sm_count;
+};
+
+bool supported(int dtype, int row_elems, int k, int space);
+size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count);
+Plan* create_plan();
+void destroy_plan(Plan* p);
+void invalidate(Plan* p);     // corpus pointer / capacity changed
+// Runs prep + contraction + fused select.  On success *partial holds S ascending
+// candidate lists per query laid out [S][B][k] inside `scratch`.
+cudaError_t launch(Plan* plan, const Problem& p, cudaStream_t st, const uint64_t** partial, int* S, int* launches);
+
+}  // namespace tensor
+}  // namespace rag

@@ -1,0 +1,158 @@
+"""DeviceStore: numpy-facing wrapper of one device-resident corpus shard.
+
+Thin by design -- argument marshalling only.  All arithmetic happens in the
+CUDA kernels behind the C ABI (include/rag_b200.h).  ctypes releases the GIL
+around every call, so FastAPI worker threads (the reference's concurrency
+model, api/routes/kb.py) overlap freely; the store's own reader/writer lock
+orders queries against upserts and deletes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class DeviceStore:
+    def __init__(self, dim: int, dtype: str = "f32", space: str = "l2", device: int = 0,
+                 capacity_hint: int = 0):
+        if space not in N.SPACES:
+            raise ValueError(f"unknown space {space!r}; expected one of {sorted(N.SPACES)}")
+        if dtype not in N.DTYPES:
+            raise ValueError(f"unknown dtype {dtype!r}; expected f32 or bf16")
+        self._lib = N.load()
+        h = C.c_void_p()
+        N.check(self._lib.rag_store_create(int(dim), N.DTYPES[dtype], N.SPACES[space], int(device),
+                                           int(capacity_hint), C.byref(h)))
+        self._h = h
+        self.dim, self.space, self.device = int(dim), space, int(device)
+        self.dtype = "bf16" if N.DTYPES[dtype] == N.DTYPE_BF16 else "f32"
+
+    # -- lifetime --------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rag_store_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- state -------------------------------------------------------------------
+    def count(self) -> int:
+        return int(self._lib.rag_store_count(self._h))
+
+    def rows(self) -> int:
+        return int(self._lib.rag_store_rows(self._h))
+
+    def capacity(self) -> int:
+        return int(self._lib.rag_store_capacity(self._h))
+
+    def kernel_launches(self) -> int:
+        return int(self._lib.rag_store_kernel_launches(self._h))
+
+    def is_live(self, row: int) -> bool:
+        return bool(self._lib.rag_store_is_live(self._h, int(row)))
+
+    def reserve(self, rows: int):
+        N.check(self._lib.rag_store_reserve(self._h, int(rows)))
+
+    # -- writes --------------------------------------------------------------------
+    def upsert(self, vectors, rows=None) -> np.ndarray:
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        if v.ndim != 2 or v.shape[1] != self.dim:
+            raise ValueError(f"vectors must be [n, {self.dim}], got {v.shape}")
+        n = v.shape[0]
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        if r is not None and r.shape != (n,):
+            raise ValueError("rows must have one entry per vector")
+        out = np.empty(n, dtype=np.int64)
+        N.check(self._lib.rag_store_upsert(self._h, n, _ptr(v), _ptr(r), _ptr(out)))
+        return out
+
+    def upsert_device(self, data_ptr: int, n: int, rows=None) -> np.ndarray:
+        """Vectors already on this store's device as fp32 [n, dim] (e.g. a torch
+        tensor's data_ptr()); used for bulk loads and synthetic corpora."""
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty(n, dtype=np.int64)
+        N.check(self._lib.rag_store_upsert_dev(self._h, int(n), C.c_void_p(int(data_ptr)), _ptr(r), _ptr(out)))
+        return out
+
+    def delete(self, rows):
+        r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
+        N.check(self._lib.rag_store_delete(self._h, r.shape[0], _ptr(r)))
+
+    def fetch(self, rows) -> np.ndarray:
+        r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
+        out = np.empty((r.shape[0], self.dim), dtype=np.float32)
+        N.check(self._lib.rag_store_fetch(self._h, r.shape[0], _ptr(r), _ptr(out)))
+        return out
+
+    # -- filters ----------------------------------------------------------------------
+    def set_mask(self, slot: int, passing: np.ndarray):
+        """`passing`: boolean array, one entry per row (shorter is fine: missing
+        rows do not pass)."""
+        b = np.ascontiguousarray(passing, dtype=bool).reshape(-1)
+        nbits = b.shape[0]
+        packed = np.packbits(b, bitorder="little")
+        pad = (-packed.shape[0]) % 8
+        if pad:
+            packed = np.concatenate([packed, np.zeros(pad, dtype=np.uint8)])
+        words = packed.view(np.uint64) if packed.shape[0] else np.zeros(0, dtype=np.uint64)
+        N.check(self._lib.rag_store_set_mask(self._h, int(slot), _ptr(words) if nbits else None, nbits))
+
+    def clear_mask(self, slot: int):
+        N.check(self._lib.rag_store_clear_mask(self._h, int(slot)))
+
+    # -- search -------------------------------------------------------------------------
+    def query(self, queries, k: int, mask_slot: int = -1, regime: str = "auto"):
+        """Returns (rows int64 [B,k], dists fp32 [B,k], counts int32 [B]); hits
+        ascending by (distance, row); unused tail has row -1 / +inf."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B, {self.dim}], got {q.shape}")
+        B = q.shape[0]
+        flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
+        rows = np.empty((B, k), dtype=np.int64)
+        dists = np.empty((B, k), dtype=np.float32)
+        counts = np.empty(B, dtype=np.int32)
+        N.check(self._lib.rag_store_query(self._h, B, _ptr(q), int(k), int(mask_slot), flags,
+                                          _ptr(rows), _ptr(dists), _ptr(counts)))
+        return rows, dists, counts
+
+    def query_device(self, queries_ptr: int, B: int, k: int, out_keys_ptr: int, stream: int = 0,
+                     mask_slot: int = -1, row_base: int = 0, regime: str = "auto"):
+        """Asynchronous shard-local search on device buffers (multi-GPU path)."""
+        flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
+        N.check(self._lib.rag_store_query_dev(self._h, int(B), C.c_void_p(int(queries_ptr)), int(k), int(mask_slot),
+                                              flags, int(row_base), C.c_void_p(int(out_keys_ptr)),
+                                              C.c_void_p(int(stream))))
+
+    def last_query_info(self):
+        ms, regime, launches = C.c_float(), C.c_int32(), C.c_int32()
+        N.check(self._lib.rag_store_last_query_info(self._h, C.byref(ms), C.byref(regime), C.byref(launches)))
+        return {"kernel_ms": ms.value, "regime": {0: None, 1: "stream", 2: "tensor"}[regime.value],
+                "launches": launches.value}
+
+
+def merge_keys_device(device: int, G: int, B: int, k: int, keys_ptr: int, out_keys_ptr: int = 0,
+                      out_rows_ptr: int = 0, out_dists_ptr: int = 0, out_counts_ptr: int = 0, stream: int = 0):
+    """Cross-shard merge of G x B x k candidate keys on the device."""
+    lib = N.load()
+    vp = lambda p: C.c_void_p(int(p)) if p else None
+    N.check(lib.rag_merge_keys_dev(int(device), int(G), int(B), int(k), vp(keys_ptr), vp(out_keys_ptr),
+                                   vp(out_rows_ptr), vp(out_dists_ptr), vp(out_counts_ptr), vp(stream)))
