@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: exact top-10 cosine search over a device-resident corpus.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU)
+
+Workload (BASELINE.json metric / configs[2]): synthetic unit-norm 10M x 768
+bf16 corpus, cosine, k = 10, one query batch per step.  The corpus is FIXED at
+10M rows and row-sharded over the N ranks (strong scaling); the per-step
+exchange is one all-gather of B x k candidate keys + the merge kernel.
+
+One JSON line on rank 0 (keys per the driver contract):
+  value     QPS with the query batch already in HBM (device-timed, CUDA events,
+            max over ranks)
+  e2e       the same metric through the public host-buffer call: pinned H2D of
+            the queries, search, D2H of the B x k result, inside the timed region
+  roofline  scan kernel: algorithmic bytes (rows x row_bytes) / its CUDA-event time
+            vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle's BLAS exact search on a bounded sample (N = 1 only)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--space", default="cosine", choices=["cosine", "l2", "ip"])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--regime", default="auto", choices=["auto", "stream", "tensor"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true", help="check one batch against a torch fp32 brute force")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_queries(n_batches, B, dim, seed=4321):
+    rng = np.random.default_rng(seed)
+    q = rng.standard_normal((n_batches, B, dim), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=2, keepdims=True)
+    return q
+
+
+def cpu_exact_qps(args, threads=None, seconds_budget=25.0):
+    """The oracle's BLAS exact search (numpy fp32 Q @ X.T + argpartition) on a
+    bounded sample of the same workload, all host cores.  Returns
+    (qps scaled to the full corpus, description)."""
+    from oracle.exact_search import fast_topk_f32, prepare_corpus
+    n = min(args.cpu_sample_rows, args.rows)
+    rng = np.random.default_rng(1234)
+    x = prepare_corpus(args.space, rng.standard_normal((n, args.dim), dtype=np.float32), args.dtype)
+    q = prepare_corpus(args.space, make_queries(1, args.batch, args.dim)[0], args.dtype)
+    fast_topk_f32(args.space, q, x[: min(n, 65536)], args.k)          # warm BLAS threads
+    t0 = time.perf_counter()
+    reps = 0
+    while True:
+        fast_topk_f32(args.space, q, x, args.k)
+        reps += 1
+        if time.perf_counter() - t0 > seconds_budget / 2 or reps >= 20:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    qps_sample = args.batch / dt
+    qps_full = qps_sample * n / args.rows
+    cores = os.cpu_count() or 1
+    return qps_full, dt, f"{n} of {args.rows} rows x {args.dim} fp32, batch {args.batch}, {reps} reps; " \
+                         f"time scaled linearly in rows", cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  Its
+    arithmetic is chromadb/hnswlib (not installable here: no wheel, no network),
+    so this arm times the oracle port -- exact brute force, which is also what
+    Chroma itself runs at the reference's shipped scale -- on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    vals, ms = [], []
+    for _ in range(min(args.warmup, 1)):
+        cpu_exact_qps(args, seconds_budget=4.0)
+    t_total0 = time.perf_counter()
+    for _ in range(steps):
+        qps, dt, sample, cores = cpu_exact_qps(args, seconds_budget=max(2.0, 60.0 / steps))
+        vals.append(qps)
+        ms.append(1e3 * args.batch / qps)
+        if time.perf_counter() - t_total0 > 150:
+            break
+    v = statistics.median(vals)
+    line = {
+        "impl": "reference", "metric": "QPS, exact top-10 cosine, 10M x 768", "value": v, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": statistics.median(ms),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "batch": args.batch, "k": args.k, "space": args.space},
+        "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return (f"synthetic unit-norm {args.rows}x{args.dim} {args.dtype} corpus, exact top-{args.k} {args.space}, "
+            f"query batch {args.batch}")
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import local_rag_system_b200 as rag
+    from local_rag_system_b200.sharded import ShardedSearcher, shard_plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- build this rank's shard on the device (synthetic, seeded per shard) ----
+    stride, counts = shard_plan(args.rows, world)
+    n_local = counts[rank]
+    store = rag.DeviceStore(args.dim, args.dtype, args.space, device=local_rank, capacity_hint=n_local)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    chunk = 500_000
+    t_build0 = time.perf_counter()
+    for s in range(0, n_local, chunk):
+        m = min(chunk, n_local - s)
+        xs = torch.randn((m, args.dim), generator=gen, device=dev, dtype=torch.float32)
+        torch.cuda.synchronize(dev)
+        store.upsert_device(xs.data_ptr(), m)      # K1 normalises + converts on the way in
+        del xs
+    build_s = time.perf_counter() - t_build0
+    assert store.count() == n_local
+
+    searcher = ShardedSearcher(store, rank, world, row_base=rank * stride)
+    B, k, K, W = args.batch, args.k, args.steps, max(args.warmup, 3)
+    q_host = torch.from_numpy(make_queries(W + K, B, args.dim)).pin_memory()
+    q_dev = q_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    if args.verify:
+        verify(args, store, searcher, q_dev[0], dev, world)
+
+    # ---- device-resident timing: `value` ----
+    for i in range(W):
+        searcher.search_device(q_dev[i], k, regime=args.regime)
+    barrier()
+    launches0 = store.kernel_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(K):
+        searcher.search_device(q_dev[W + i], k, regime=args.regime)
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = ev[0].elapsed_time(ev[K])
+    per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
+    launches = store.kernel_launches() - launches0 + K          # + the cross-shard merge kernel per step
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = B * K / (total_ms / 1e3)
+
+    # ---- end to end through the host-buffer API: `e2e` ----
+    for i in range(W):
+        searcher.search(q_host[i].numpy(), k, regime=args.regime)
+    barrier()
+    t0 = time.perf_counter()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lat = []
+    for i in range(K):
+        ts = time.perf_counter()
+        searcher.search(q_host[W + i].numpy(), k, regime=args.regime)
+        lat.append((time.perf_counter() - ts) * 1e3)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * K / (float(t.item()) / 1e3)
+    lat.sort()
+
+    # ---- roofline of the dominant kernel (scan), CUDA events on its own stream ----
+    kms = []
+    regime_seen = None
+    for i in range(min(K, 50)):
+        store.query(q_host[W + i].numpy(), k, regime=args.regime)
+        info = store.last_query_info()
+        kms.append(info["kernel_ms"])
+        regime_seen = info["regime"]
+    kernel_ms = statistics.mean(kms)
+    pk = peaks()
+    row_bytes = args.dim * (2 if args.dtype == "bf16" else 4)
+    if regime_seen == "tensor":
+        flops = 2.0 * B * n_local * args.dim
+        achieved = flops / (kernel_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " burst",
+                "kernel": "gemm_topk", "kernel_ms": kernel_ms}
+    else:
+        alg_bytes = float(n_local) * row_bytes + n_local / 8.0
+        achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                "kernel": "scan_stream_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
+                "frac_of_8TBs_nominal": achieved / 8000.0}
+
+    if rank == 0:
+        line = {
+            "metric": "QPS, exact top-10 cosine, 10M x 768", "value": value, "unit": "queries/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "batch": B, "k": k, "space": args.space,
+                       "rows_per_gpu": n_local, "sharding": f"row-wise x{world}, all-gather of Bxk keys + merge kernel",
+                       "regime": regime_seen, "l2_flush": "inputs larger than L2 (shard bytes >> 126 MB)",
+                       "build_seconds": round(build_s, 2)},
+            "p50_ms": per_step[len(per_step) // 2], "p95_ms": per_step[int(len(per_step) * 0.95)],
+            "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * args.dim * 4,
+                    "d2h_bytes_per_step": B * k * 12 + B * 4, "p50_ms": lat[len(lat) // 2],
+                    "p95_ms": lat[int(len(lat) * 0.95)]},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            qps, dt, sample, cores = cpu_exact_qps(args)
+            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                                    "sample": sample}
+        print(json.dumps(line))
+    store.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def verify(args, store, searcher, q, dev, world):
+    """One batch against a chunked torch fp32 brute force over this rank's shard
+    (rank-local check; cross-shard merge equality is covered by the tests)."""
+    import torch
+    rows, dists, counts = store.query(q.cpu().numpy(), args.k, regime=args.regime)
+    n = store.rows()
+    qp = torch.nn.functional.normalize(q, dim=1) if args.space == "cosine" else q
+    if args.dtype == "bf16":
+        qp = qp.to(torch.bfloat16).float()
+    best_d = torch.full((q.shape[0], 0), float("inf"), device=dev)
+    best_r = torch.zeros((q.shape[0], 0), dtype=torch.int64, device=dev)
+    for s in range(0, n, 200_000):
+        idx = np.arange(s, min(n, s + 200_000))
+        x = torch.from_numpy(store.fetch(idx)).to(dev)
+        d = 1.0 - qp @ x.T if args.space != "l2" else torch.cdist(qp, x) ** 2
+        best_d = torch.cat([best_d, d], 1)
+        best_r = torch.cat([best_r, torch.from_numpy(idx).to(dev)[None, :].expand(q.shape[0], -1)], 1)
+        o = torch.argsort(best_d, dim=1)[:, :args.k]
+        best_d, best_r = torch.gather(best_d, 1, o), torch.gather(best_r, 1, o)
+    ok = np.array_equal(best_r.cpu().numpy(), rows) or np.allclose(best_d.cpu().numpy(), dists, rtol=1e-5, atol=2e-6)
+    print(f"[verify] rank-local top-{args.k} vs torch fp32 brute force: {'OK' if ok else 'MISMATCH'}", file=sys.stderr)
+    if not ok:
+        raise SystemExit("verification failed")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,103 @@
+"""Row-sharded exact search over the GPUs of one box (K6).
+
+One process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  The corpus
+is split row-wise into contiguous shards; rank g owns global rows
+[g * stride, g * stride + rows_g).  A query batch is replicated to every rank,
+each rank runs the shard-local scan + fused top-k (no data-path collective),
+and the only exchange is one all-gather of B x k 64-bit candidate keys per
+rank (80 B per rank for B=1, k=10) followed by the merge kernel.  Because keys
+carry global rows, the merged result is bit-identical to what a single store
+holding the whole corpus returns -- ties included.
+
+torch is used for what it is good at here: device buffers, streams and the
+process group.  The scan, select and merge are the engine's own kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import DeviceStore, merge_keys_device
+
+
+def shard_plan(total_rows: int, world: int) -> Tuple[int, list]:
+    """Contiguous row split: returns (stride, [rows per rank]).  stride =
+    ceil(total / world) is also each rank's global row base multiplier."""
+    stride = (total_rows + world - 1) // world
+    counts = [max(0, min(stride, total_rows - g * stride)) for g in range(world)]
+    if stride * world >= 2 ** 32:
+        raise ValueError("global rows must stay below 2^32 (keys carry 32-bit rows)")
+    return stride, counts
+
+
+def exchange_candidates(local_keys: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """All-gather of per-shard candidate keys.  local_keys: int64 [B*k] (the
+    uint64 key bits) on the rank's device (or CPU under gloo, for tests).
+    Returns int64 [world, B*k], identical on every rank."""
+    out = torch.empty((world,) + tuple(local_keys.shape), dtype=local_keys.dtype, device=local_keys.device)
+    if world == 1:
+        out[0].copy_(local_keys)
+        return out
+    dist.all_gather_into_tensor(out.view(-1), local_keys.contiguous().view(-1), group=group)
+    return out
+
+
+class ShardedSearcher:
+    """Search front-end of one rank.  Every rank must call search*() with the
+    same queries (the query batch is replicated)."""
+
+    def __init__(self, store: DeviceStore, rank: int = 0, world: int = 1, row_base: int = 0, group=None):
+        self.store, self.rank, self.world, self.row_base, self.group = store, rank, world, int(row_base), group
+        self.device = torch.device("cuda", store.device)
+        self._buf = {}
+
+    def _buffers(self, B: int, k: int):
+        key = (B, k)
+        b = self._buf.get(key)
+        if b is None:
+            dev = self.device
+            b = {
+                "local": torch.empty(B * k, dtype=torch.int64, device=dev),
+                "rows": torch.empty((B, k), dtype=torch.int64, device=dev),
+                "dists": torch.empty((B, k), dtype=torch.float32, device=dev),
+                "counts": torch.empty(B, dtype=torch.int32, device=dev),
+                "q": torch.empty((B, self.store.dim), dtype=torch.float32, device=dev),
+                "h_rows": torch.empty((B, k), dtype=torch.int64).pin_memory(),
+                "h_dists": torch.empty((B, k), dtype=torch.float32).pin_memory(),
+                "h_counts": torch.empty(B, dtype=torch.int32).pin_memory(),
+            }
+            self._buf[key] = b
+        return b
+
+    def search_device(self, q_dev: torch.Tensor, k: int, mask_slot: int = -1, regime: str = "auto"):
+        """q_dev: fp32 [B, dim] on this rank's device.  Asynchronous on the current
+        stream.  Returns device tensors (global rows int64 [B,k], dists fp32 [B,k],
+        counts int32 [B])."""
+        B = q_dev.shape[0]
+        b = self._buffers(B, k)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.store.query_device(q_dev.data_ptr(), B, k, b["local"].data_ptr(), stream=stream,
+                                mask_slot=mask_slot, row_base=self.row_base, regime=regime)
+        gathered = exchange_candidates(b["local"], self.world, self.group)
+        merge_keys_device(self.store.device, self.world, B, k, gathered.data_ptr(), 0, b["rows"].data_ptr(),
+                          b["dists"].data_ptr(), b["counts"].data_ptr(), stream=stream)
+        return b["rows"], b["dists"], b["counts"]
+
+    def search(self, queries: np.ndarray, k: int, mask_slot: int = -1, regime: str = "auto"):
+        """Host-to-host call: pinned H2D of the queries, shard search, exchange,
+        merge, D2H of the final B x k result.  Returns numpy (rows, dists, counts)."""
+        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
+        if q.ndim == 1:
+            q = q[None, :]
+        B = q.shape[0]
+        b = self._buffers(B, k)
+        b["q"].copy_(q if q.is_pinned() else q.pin_memory(), non_blocking=True)
+        rows, dists, counts = self.search_device(b["q"], k, mask_slot, regime)
+        b["h_rows"].copy_(rows, non_blocking=True)
+        b["h_dists"].copy_(dists, non_blocking=True)
+        b["h_counts"].copy_(counts, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return b["h_rows"].numpy().copy(), b["h_dists"].numpy().copy(), b["h_counts"].numpy().copy()

@@ -191,6 +191,8 @@ def _cmp(op: str, have, want) -> bool:
         return present and any(_same_type(have, w) and have == w for w in want)
     if op == "$nin":
         return not (present and any(_same_type(have, w) and have == w for w in want))
+    if isinstance(want, (bool, str)) or not isinstance(want, (int, float)):
+        raise ValueError(f"Expected operand of {op} to be an int or a float, got {want!r}")
     if not present or isinstance(have, (bool, str)) or not _same_type(have, want):
         return False
     return {"$gt": have > want, "$gte": have >= want, "$lt": have < want, "$lte": have <= want}[op]

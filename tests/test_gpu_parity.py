@@ -1,0 +1,237 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  GPU only.
+
+Bars (BASELINE.json north_star):
+  fp32 store : returned rows identical to the fp64-accumulated oracle except
+               ties within 1e-6; distances within 1e-5 relative + 1e-6 absolute.
+  bf16 store : same inputs (the bf16-rounded vectors) -> recall@k >= 0.999.
+"""
+import numpy as np
+import pytest
+
+from local_rag_system_b200 import DeviceStore
+from oracle.exact_search import exact_search, prepare_corpus, round_to_bf16
+from tests.conftest import unit_rows
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL, TIE = 1e-5, 1e-6, 1e-6
+
+
+def check_against_oracle(space, dtype, x, q, k, rows, dists, counts, valid=None, min_recall=1.0):
+    """rows/dists/counts from the engine vs exact fp64 search on the same inputs."""
+    orows, od = exact_search(space, q, x, k, valid, dtype)
+    hits = total = 0
+    for b in range(q.shape[0]):
+        n = len(orows[b])
+        assert counts[b] == n, f"query {b}: count {counts[b]} != {n}"
+        assert np.all(rows[b, n:] == -1) and np.all(np.isinf(dists[b, n:]))
+        got_r, got_d = rows[b, :n], dists[b, :n].astype(np.float64)
+        assert np.all(np.diff(got_d) >= 0), f"query {b}: distances not ascending"
+        assert np.allclose(got_d, od[b], rtol=RTOL, atol=ATOL), \
+            f"query {b}: max dist err {np.max(np.abs(got_d - od[b]))}"
+        assert len(set(got_r.tolist())) == n
+        if valid is not None:
+            assert np.all(valid[got_r])
+        for j in range(n):
+            total += 1
+            if got_r[j] == orows[b][j]:
+                hits += 1
+            elif got_r[j] in orows[b]:
+                hits += 1          # same set, order swapped inside a tie
+            else:
+                # allowed only when it ties (within TIE) with the oracle's boundary
+                if abs(got_d[j] - od[b][-1]) <= TIE + RTOL * abs(od[b][-1]) and min_recall >= 1.0:
+                    hits += 1
+    recall = hits / max(total, 1)
+    assert recall >= min_recall, f"recall {recall}"
+    return recall
+
+
+CASES = [
+    # space, dtype, n, dim, B, k
+    ("l2", "f32", 1000, 384, 1, 5),
+    ("l2", "f32", 5000, 384, 3, 10),
+    ("cosine", "f32", 5000, 384, 8, 10),
+    ("ip", "f32", 3000, 768, 2, 10),
+    ("cosine", "bf16", 5000, 768, 1, 10),
+    ("cosine", "bf16", 5000, 768, 4, 10),
+    ("l2", "bf16", 3000, 384, 5, 20),
+    ("ip", "bf16", 3000, 1024, 2, 7),
+    ("l2", "f32", 777, 3, 2, 4),          # the reference tests' dummy 3-d embeddings
+    ("cosine", "f32", 999, 17, 3, 9),
+    ("cosine", "bf16", 999, 100, 6, 33),
+    ("l2", "f32", 2000, 512, 7, 100),
+    ("cosine", "f32", 4096, 256, 20, 10),  # > 8 queries: several corpus passes in the stream regime
+    ("l2", "bf16", 2500, 1536, 3, 64),
+    ("cosine", "f32", 300, 1024, 1, 300),  # k == n
+]
+
+
+@pytest.mark.parametrize("space,dtype,n,dim,B,k", CASES)
+def test_search_matches_oracle(space, dtype, n, dim, B, k):
+    rng = np.random.default_rng(n + dim + B + k)
+    x = rng.standard_normal((n, dim)).astype(np.float32) if space != "cosine" else unit_rows(n, dim, n)
+    q = rng.standard_normal((B, dim)).astype(np.float32)
+    q[0] = x[n // 2] + 0.01 * rng.standard_normal(dim).astype(np.float32)   # a planted near neighbour
+    if dtype == "bf16":
+        # same inputs on both sides: values exactly representable in bf16
+        x, q = round_to_bf16(prepare_corpus(space, x)), round_to_bf16(prepare_corpus(space, q))
+    st = DeviceStore(dim, dtype, space)
+    try:
+        out = st.upsert(x)
+        assert out.tolist() == list(range(n)) and st.count() == n and st.rows() == n
+        stored = st.fetch(np.arange(n))
+        assert np.allclose(stored, prepare_corpus(space, x, dtype), rtol=0, atol=2e-7 if dtype == "f32" else 0)
+        rows, dists, counts = st.query(q, k, regime="stream")
+        check_against_oracle(space, dtype, stored, q, k, rows, dists, counts,
+                             min_recall=1.0 if dtype == "f32" else 0.999)
+        assert st.last_query_info()["regime"] == "stream" and st.kernel_launches() > 0
+    finally:
+        st.close()
+
+
+def test_tombstones_masks_and_row_reuse():
+    n, dim, k = 4000, 384, 10
+    x = unit_rows(n, dim, 7)
+    q = unit_rows(5, dim, 8)
+    rng = np.random.default_rng(9)
+    st = DeviceStore(dim, "f32", "l2")
+    try:
+        st.upsert(x)
+        dead = rng.choice(n, size=n // 20, replace=False)
+        st.delete(dead)
+        st.delete(dead[:10])                       # deleting a dead row is a no-op
+        live = np.ones(n, bool)
+        live[dead] = False
+        assert st.count() == int(live.sum())
+        rows, dists, counts = st.query(q, k)
+        check_against_oracle("l2", "f32", x, q, k, rows, dists, counts, valid=live)
+        for sel in (0.5, 0.1, 0.01, 0.0):
+            passing = rng.random(n) < sel
+            st.set_mask(3, passing)
+            rows, dists, counts = st.query(q, k, mask_slot=3)
+            check_against_oracle("l2", "f32", x, q, k, rows, dists, counts, valid=live & passing)
+        st.set_mask(4, np.ones(100, bool))         # a mask shorter than the store: missing rows do not pass
+        rows, dists, counts = st.query(q, k, mask_slot=4)
+        short = np.zeros(n, bool)
+        short[:100] = True
+        check_against_oracle("l2", "f32", x, q, k, rows, dists, counts, valid=live & short)
+        # new rows land in freed slots; explicit rows overwrite in place
+        fresh = unit_rows(7, dim, 11)
+        got = st.upsert(fresh)
+        assert set(got.tolist()) <= set(dead.tolist()) and st.rows() == n
+        x[got] = fresh
+        live[got] = True
+        x[5] = fresh[0]
+        assert st.upsert(fresh[:1], rows=[5]).tolist() == [5]
+        rows, dists, counts = st.query(np.vstack([q, fresh[:2]]), k)
+        check_against_oracle("l2", "f32", x, np.vstack([q, fresh[:2]]), k, rows, dists, counts, valid=live)
+        with pytest.raises(ValueError):
+            st.upsert(fresh[:1], rows=[n + 5])
+        with pytest.raises(ValueError):
+            st.query(q, k, mask_slot=9)            # unset slot
+    finally:
+        st.close()
+
+
+def test_edge_cases():
+    st = DeviceStore(8, "f32", "l2")
+    try:
+        q = np.ones((2, 8), np.float32)
+        rows, dists, counts = st.query(q, 5)                       # empty store
+        assert counts.tolist() == [0, 0] and np.all(rows == -1) and np.all(np.isinf(dists))
+        st.upsert(np.eye(8, dtype=np.float32)[:3])
+        rows, dists, counts = st.query(q, 5)                       # k > live rows
+        assert counts.tolist() == [3, 3] and rows[0, :3].tolist() == [0, 1, 2] and np.all(rows[:, 3:] == -1)
+        assert np.allclose(dists[0, :3], 7.0)                      # exact ties -> row order
+        st.delete([0, 1, 2])
+        rows, dists, counts = st.query(q, 5)                       # everything deleted
+        assert counts.tolist() == [0, 0]
+        for bad_k in (0, -1, 2000):
+            with pytest.raises(ValueError):
+                st.query(q, bad_k)
+        with pytest.raises(ValueError):
+            st.query(np.ones((1, 9), np.float32), 1)
+    finally:
+        st.close()
+
+
+def test_growth_keeps_rows(monkeypatch):
+    dim = 64
+    st = DeviceStore(dim, "bf16", "cosine", capacity_hint=0)
+    try:
+        parts = [round_to_bf16(unit_rows(700, dim, s)) for s in range(6)]   # crosses the 1024/2048/4096 reallocations
+        for p in parts:
+            st.upsert(p)
+        x = np.vstack(parts)
+        assert st.count() == x.shape[0] and st.capacity() >= x.shape[0]
+        assert np.array_equal(st.fetch(np.arange(x.shape[0])), prepare_corpus("cosine", x, "bf16"))
+        q = round_to_bf16(unit_rows(3, dim, 99))
+        rows, dists, counts = st.query(q, 10)
+        check_against_oracle("cosine", "bf16", st.fetch(np.arange(x.shape[0])), q, 10, rows, dists, counts,
+                             min_recall=0.999)
+    finally:
+        st.close()
+
+
+def test_duplicate_vectors_tie_break_by_row():
+    dim = 384
+    base = unit_rows(50, dim, 3)
+    x = np.vstack([base, base, base])          # every vector three times
+    st = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        rows, dists, counts = st.query(base[:4], 3)
+        for b in range(4):
+            assert rows[b].tolist() == [b, b + 50, b + 100]
+            assert np.allclose(dists[b], 0.0, atol=1e-6)
+    finally:
+        st.close()
+
+
+def test_large_streaming_properties():
+    """Config-2 scale (1M x 384 fp32, cosine, top-10) through size-independent
+    properties: planted neighbours are found at rank 1 with the right distance,
+    results are sorted, a full-corpus query equals the merge of two half-corpus
+    queries (masks), and deleting the winner promotes the runner-up."""
+    n, dim, k = 1_000_000, 384, 10
+    rng = np.random.default_rng(1234)
+    st = DeviceStore(dim, "f32", "cosine", capacity_hint=n)
+    try:
+        chunk = 125_000
+        keep = {}
+        for s in range(0, n, chunk):
+            xs = rng.standard_normal((chunk, dim), dtype=np.float32)
+            st.upsert(xs)
+            for r in (s + 17, s + chunk - 1):
+                keep[r] = xs[r - s].copy()
+        assert st.count() == n
+        planted = sorted(keep)
+        q = np.stack([keep[r] + 0.02 * rng.standard_normal(dim).astype(np.float32) for r in planted])
+        rows, dists, counts = st.query(q, k)
+        assert np.all(counts == k)
+        assert rows[:, 0].tolist() == planted
+        qn = q / np.linalg.norm(q, axis=1, keepdims=True)
+        for b, r in enumerate(planted):
+            xr = keep[r] / np.linalg.norm(keep[r])
+            assert abs(dists[b, 0] - (1.0 - float(qn[b].astype(np.float64) @ xr.astype(np.float64)))) < 1e-6
+        assert np.all(np.diff(dists, axis=1) >= 0)
+        # split by parity of the row: top-k(all) == merge(top-k(even), top-k(odd))
+        even = (np.arange(n) % 2) == 0
+        st.set_mask(0, even)
+        st.set_mask(1, ~even)
+        r0, d0, _ = st.query(q, k, mask_slot=0)
+        r1, d1, _ = st.query(q, k, mask_slot=1)
+        assert np.all(r0 % 2 == 0) and np.all(r1 % 2 == 1)
+        for b in range(q.shape[0]):
+            allr = np.concatenate([r0[b], r1[b]])
+            alld = np.concatenate([d0[b], d1[b]])
+            o = np.lexsort((allr, alld))[:k]
+            assert allr[o].tolist() == rows[b].tolist()
+            assert np.array_equal(alld[o], dists[b])
+        # delete the winners: the former runner-up is now first
+        st.delete(rows[:, 0])
+        r2, d2, _ = st.query(q, k)
+        assert np.array_equal(r2[:, :k - 1], rows[:, 1:]) and np.array_equal(d2[:, :k - 1], dists[:, 1:])
+    finally:
+        st.close()
