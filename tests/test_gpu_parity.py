@@ -42,7 +42,7 @@ def check_against_oracle(space, dtype, x, q, k, rows, dists, counts, valid=None,
                 # allowed only when it ties (within TIE) with the oracle's boundary
                 if abs(got_d[j] - od[b][-1]) <= TIE + RTOL * abs(od[b][-1]) and min_recall >= 1.0:
                     hits += 1
-    recall = hits / max(total, 1)
+    recall = hits / total if total else 1.0
     assert recall >= min_recall, f"recall {recall}"
     return recall
 
