@@ -1,11 +1,538 @@
-// placeholder until the tcgen05 kernel lands (see gemm_topk.cu)
+// K3 + K4: tensor-core search regime for large query batches.
+//
+// Replaces, for B > 8 queries, the hnswlib graph walk / numpy brute force behind
+// collection.query (api/app.py:544-549) with an exact dense contraction
+// Q[B x D] . X[N x D]^T on the 5th-generation tensor cores, with the top-k
+// selection fused into the epilogue so the B x N score matrix never exists.
+//
+// Design (sm_100a only; tcgen05 + TMEM + TMA):
+//   * one persistent CTA per SM, dedicated for its whole life to ONE tile of 128
+//     queries (the MMA M dimension).  The 128 x D bf16 query tile is loaded ONCE
+//     into TENSOR MEMORY (D/2 columns) and used as the A operand from TMEM
+//     (tcgen05.mma ... [d_tmem], [a_tmem], b_desc): the queries never touch shared
+//     memory or L2 again, so on-chip traffic is the corpus stream only.
+//   * the corpus streams HBM -> TMA (128B-swizzled boxes of 64 rows x 64 elements)
+//     -> a 12-stage / 192 KB shared-memory ring -> tcgen05.mma as the B operand.
+//     Every corpus byte is read from HBM once per batch (CTAs serving different
+//     query tiles walk the corpus tiles in the same order, so re-reads hit L2).
+//   * accumulators: 2 x 64 fp32 columns of TMEM (double buffered): while the
+//     tensor core contracts corpus tile i+1, four epilogue warps drain tile i with
+//     tcgen05.ld (thread = one query, 64 scores), test them against the query's
+//     running k-th best distance and insert the rare survivors into a per-thread
+//     sorted list (registers for k <= 16).  live/filter bitmaps are applied on the
+//     survivor path; tiles whose 64 rows are all dead or filtered are skipped.
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and
+//     TMEM owner, warps 2-5 = epilogue.
+//
+// Roofline: HBM for B <= ~256 (corpus read once, 2 x 128 x 64 x 16 MACs per 2 KB of
+// stage), tensor pipe beyond.  Algorithmic FLOPs = 2 B N D.
 #include "tensor_regime.h"
-namespace rag { namespace tensor {
-struct Plan { int dummy; };
-bool supported(int, int, int, int) { return false; }
-size_t scratch_bytes(int, int, int, int, int) { return 0; }
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rag {
+namespace tensor {
+
+namespace {
+
+constexpr int kM = 128;              // queries per CTA (MMA M)
+constexpr int kNB = 64;              // corpus rows per tile (MMA N)
+constexpr int kAtomK = 64;           // bf16 elements per 128-byte swizzle atom row
+constexpr int kStageK = 128;         // K elements per pipeline stage (two atoms)
+constexpr int kAtomBytes = kNB * kAtomK * 2;          // 8 KB
+constexpr int kStageBytes = 2 * kAtomBytes;            // 16 KB
+constexpr int kStages = 12;                            // 192 KB in flight per SM
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr int kTmemCols = 512;
+constexpr int kMaxKCols = 384;       // A operand: up to 768 bf16 per query
+constexpr int kAccCols = kNB;        // fp32 accumulator columns per buffer
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+
+// ---- PTX wrappers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T ; A is 128 x 16 bf16 (8 columns), B is kNB x 16 bf16 K-major
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// shared-memory matrix descriptor: K-major operand, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);        // start address
+  d |= static_cast<uint64_t>(1) << 16;                           // leading byte offset (ignored for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride byte offset: next 8-row group
+  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = kNB
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kNB >> 3) << 17) |
+                            (static_cast<uint32_t>(kM >> 4) << 24);
+
+struct Args {
+  const __nv_bfloat16* q_bf16;   // [n_mtiles*128][row_elems] prepared queries, zero rows beyond B
+  const float* q_norm2;          // [n_mtiles*128]
+  const float* x_norm2;          // [n_rows] (l2)
+  const uint32_t* live;
+  const uint32_t* filter;
+  int64_t filter_words;
+  int64_t n_rows;
+  int row_elems;
+  int B, k;
+  int cpm;                       // CTAs per query tile
+  uint64_t* partial;             // [cpm][B][k]
+};
+
+// per-thread running top-k.  KL <= 16: registers (fully unrolled); larger: local memory.
+template <int KL>
+struct TopList {
+  uint64_t e[KL];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < KL; ++i) e[i] = kEmptyKey;
+  }
+  __device__ __forceinline__ uint64_t kth(int k) const {
+    if constexpr (KL <= 16) {
+      uint64_t t = e[KL - 1];
+#pragma unroll
+      for (int i = 0; i < KL; ++i) t = (i == k - 1) ? e[i] : t;
+      return t;
+    } else {
+      return e[k - 1];
+    }
+  }
+  // precondition: key < kth(k)
+  __device__ __forceinline__ void insert(uint64_t key, int k) {
+    if constexpr (KL <= 16) {
+#pragma unroll
+      for (int i = 0; i < KL; ++i) {
+        const uint64_t cur = e[i];
+        const bool lt = key < cur;
+        e[i] = lt ? key : cur;
+        key = lt ? cur : key;
+      }
+    } else {
+      int i = k - 1;
+      while (i > 0 && e[i - 1] > key) { e[i] = e[i - 1]; --i; }
+      e[i] = key;
+    }
+  }
+};
+
+template <int KL, bool L2>
+__global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;             // 1024-byte aligned stage ring
+  const uint32_t bar_base = base + kStages * kStageBytes;
+  // barrier layout (8 bytes each): full[kStages], empty[kStages], acc_full[2], acc_empty[2], tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto accf_bar = [&](int b) { return bar_base + 8u * (2 * kStages + b); };
+  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.y;                 // query tile
+  const int cj = blockIdx.x;                 // position among the CTAs of this query tile
+  const int64_t n_tiles = (a.n_rows + kNB - 1) / kNB;
+  const int kcols = ((a.row_elems + 15) / 16) * 8;         // TMEM columns of the A operand
+  const int k_steps = (a.row_elems + 15) / 16;             // MMAs per tile
+  const int n_stages_per_tile = (a.row_elems + kStageK - 1) / kStageK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(kMaxKCols);   // accumulators after the A columns
+
+  auto tile_mask = [&](int64_t t, uint32_t& w0, uint32_t& w1) {
+    w0 = __ldg(a.live + 2 * t);
+    w1 = __ldg(a.live + 2 * t + 1);
+    if (a.filter != nullptr) {
+      w0 &= (2 * t < a.filter_words) ? __ldg(a.filter + 2 * t) : 0u;
+      w1 &= (2 * t + 1 < a.filter_words) ? __ldg(a.filter + 2 * t + 1) : 0u;
+    }
+  };
+
+  if (warp >= kEpiWarp0) {
+    // ================= epilogue warps: load A into TMEM, then drain accumulators =================
+    const int lg = warp & 3;                       // TMEM lane group this warp may access
+    const int m = lg * 32 + lane;                  // query row inside the tile
+    const int b = mt * kM + m;                     // global query index
+    const bool q_valid = b < a.B;
+    {
+      const uint4* qrow = reinterpret_cast<const uint4*>(a.q_bf16 + static_cast<size_t>(mt * kM + m) * a.row_elems);
+      const int chunks = a.row_elems / 8;          // 16-byte chunks in the row (row_elems % 8 == 0)
+      for (int c0 = 0; c0 < kcols; c0 += 8) {      // 8 TMEM columns = 16 bf16 = two 16-byte chunks
+        uint32_t v[8];
+        const int ch = c0 / 4;
+        uint4 lo = (ch < chunks) ? __ldg(qrow + ch) : make_uint4(0, 0, 0, 0);
+        uint4 hi = (ch + 1 < chunks) ? __ldg(qrow + ch + 1) : make_uint4(0, 0, 0, 0);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        tmem_st_x8(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(c0), v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+    }
+    asm volatile("bar.sync 1, 160;" ::: "memory");   // epilogue warps (128) + MMA warp (32): A operand is in TMEM
+
+    TopList<KL> top;
+    top.init();
+    const int k = a.k;
+    float tau = __int_as_float(0x7f800000);          // +inf until the list is full
+    uint64_t kth_key = kEmptyKey;
+    const float qn = (L2 && q_valid) ? a.q_norm2[b] : 0.0f;
+
+    uint32_t it = 0;
+    for (int64_t t = cj; t < n_tiles; t += a.cpm) {
+      uint32_t w0, w1;
+      tile_mask(t, w0, w1);
+      if ((w0 | w1) == 0u) continue;                 // tile skipped by every role
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      ++it;
+      float xn0 = 0.0f, xn1 = 0.0f;
+      if constexpr (L2) {
+        const int64_t r0 = t * kNB + lane, r1 = r0 + 32;
+        xn0 = (r0 < a.n_rows) ? __ldg(a.x_norm2 + r0) : 0.0f;
+        xn1 = (r1 < a.n_rows) ? __ldg(a.x_norm2 + r1) : 0.0f;
+      }
+      mbar_wait(accf_bar(buf), par);
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld_x32(tmem_acc + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(buf * kAccCols + half * 32), v);
+        tmem_wait_ld();
+        if (half == 1) {                             // both halves are in registers: release the buffer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acce_bar(buf));
+        }
+        float d[32];
+        uint32_t cand = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dot = __uint_as_float(v[j]);
+          if constexpr (L2) {
+            const float xn = __shfl_sync(0xffffffffu, half ? xn1 : xn0, j);
+            d[j] = fmaf(-2.0f, dot, qn + xn);
+          } else {
+            d[j] = 1.0f - dot;
+          }
+          cand |= (d[j] <= tau) ? (1u << j) : 0u;
+        }
+        cand &= half ? w1 : w0;                      // live & filter bits of these 32 rows
+        if (!q_valid) cand = 0;
+        while (cand) {
+          const int j = __ffs(cand) - 1;
+          cand &= cand - 1;
+          float dj = 0.0f;
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) dj = (jj == j) ? d[jj] : dj;
+          if (L2) dj = fmaxf(dj, 0.0f);
+          const uint64_t key = make_key(dj, static_cast<uint32_t>(t * kNB + half * 32 + j));
+          if (key < kth_key) {
+            top.insert(key, k);
+            kth_key = top.kth(k);
+            tau = (kth_key == kEmptyKey) ? __int_as_float(0x7f800000) : key_dist(kth_key);
+          }
+        }
+      }
+    }
+    // ---- emit this thread's list: partial[cj][b][0..k) ----
+    if (q_valid) {
+      uint64_t* out = a.partial + (static_cast<size_t>(cj) * a.B + b) * k;
+      if constexpr (KL <= 16) {
+#pragma unroll
+        for (int i = 0; i < KL; ++i) if (i < k) out[i] = top.e[i];
+      } else {
+        for (int i = 0; i < k; ++i) out[i] = top.e[i];
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      for (int64_t t = cj; t < n_tiles; t += a.cpm) {
+        uint32_t w0, w1;
+        tile_mask(t, w0, w1);
+        if ((w0 | w1) == 0u) continue;
+        const int row0 = static_cast<int>(t * kNB);
+        for (int ks = 0; ks < n_stages_per_tile; ++ks) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int k0 = ks * kStageK;
+          const bool two = (k0 + kAtomK) < a.row_elems;
+          mbar_arrive_expect_tx(full_bar(s), two ? kStageBytes : kAtomBytes);
+          const uint32_t dst = base + s * kStageBytes;
+          tma_load_2d(dst, &tmap, full_bar(s), k0, row0);
+          if (two) tma_load_2d(dst + kAtomBytes, &tmap, full_bar(s), k0 + kAtomK, row0);
+          if (++s == kStages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ================= MMA issuer (warp 1) =================
+    asm volatile("bar.sync 1, 160;" ::: "memory");   // wait for the A operand
+    tc_fence_after();
+    uint32_t s = 0, ph = 0, it = 0;
+    for (int64_t t = cj; t < n_tiles; t += a.cpm) {
+      uint32_t w0, w1;
+      tile_mask(t, w0, w1);
+      if ((w0 | w1) == 0u) continue;
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      ++it;
+      mbar_wait(acce_bar(buf), par ^ 1u);           // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_acc + static_cast<uint32_t>(buf * kAccCols);
+      int kk = 0;
+      for (int ks = 0; ks < n_stages_per_tile; ++ks) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t stage = base + s * kStageBytes;
+#pragma unroll
+          for (int j = 0; j < kStageK / 16; ++j) {
+            if (kk < k_steps) {
+              const uint32_t b_addr = stage + (j >> 2) * kAtomBytes + (j & 3) * 32;
+              umma_ts(d_tmem, tmem_base + static_cast<uint32_t>(kk * 8), make_b_desc(b_addr), kIdesc, kk > 0 ? 1u : 0u);
+            }
+            ++kk;
+          }
+          umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+          if (ks == n_stages_per_tile - 1) umma_commit(accf_bar(buf));
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side --------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct Layout {
+  int n_mtiles, cpm;
+  size_t off_qbf16, off_qnorm, off_qf32, off_partial, total;
+};
+
+Layout make_layout(int row_elems, int B, int k, int sm_count) {
+  Layout L{};
+  L.n_mtiles = (B + kM - 1) / kM;
+  L.cpm = sm_count / L.n_mtiles;
+  if (L.cpm < 1) L.cpm = 1;
+  size_t off = 0;
+  L.off_qbf16 = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * row_elems * 2);
+  L.off_qnorm = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);
+  L.off_qf32 = off;  off += align256(static_cast<size_t>(B) * row_elems * 4);
+  L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
+  L.total = off;
+  return L;
+}
+
+template <int KL>
+cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, dim3 grid, cudaStream_t st) {
+  cudaError_t e;
+  if (l2) {
+    e = cudaFuncSetAttribute(gemm_topk_kernel<KL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    gemm_topk_kernel<KL, true><<<grid, kThreads, kSmemBytes, st>>>(tmap, a);
+  } else {
+    e = cudaFuncSetAttribute(gemm_topk_kernel<KL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    gemm_topk_kernel<KL, false><<<grid, kThreads, kSmemBytes, st>>>(tmap, a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+struct Plan { int unused; };
+
+bool supported(int dtype, int row_elems, int k, int space) {
+  (void)space;
+  return dtype == 1 /*bf16*/ && row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && k >= 1 && k <= 1024 &&
+         get_encode() != nullptr;
+}
+
+size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count) {
+  if (dtype != 1) return 0;
+  return make_layout(row_elems, B, k, sm_count).total;
+}
+
 Plan* create_plan() { return new Plan(); }
 void destroy_plan(Plan* p) { delete p; }
 void invalidate(Plan*) {}
-cudaError_t launch(Plan*, const Problem&, cudaStream_t, const uint64_t**, int*, int*) { return cudaErrorNotSupported; }
-}}
+
+cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, const uint64_t** partial, int* S, int* launches) {
+  if (!supported(p.dtype, p.row_elems, p.k, p.space)) return cudaErrorNotSupported;
+  const Layout L = make_layout(p.row_elems, p.B, p.k, p.sm_count);
+  __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(p.scratch + L.off_qbf16);
+  float* q_norm = reinterpret_cast<float*>(p.scratch + L.off_qnorm);
+  float* q_f32 = reinterpret_cast<float*>(p.scratch + L.off_qf32);
+  uint64_t* part = reinterpret_cast<uint64_t*>(p.scratch + L.off_partial);
+
+  // queries: zero the padded tile rows, then normalise / round / convert
+  cudaError_t e = cudaMemsetAsync(q_bf16, 0, static_cast<size_t>(L.n_mtiles) * kM * p.row_elems * 2, st);
+  if (e != cudaSuccess) return e;
+  PrepArgs pa{};
+  pa.src = p.queries_raw; pa.B = p.B; pa.dim = p.dim; pa.row_elems = p.row_elems;
+  pa.normalise = (p.space == 1); pa.round_bf16 = 1;
+  pa.q_f32 = q_f32; pa.q_bf16 = q_bf16; pa.q_norm2 = q_norm;
+  e = launch_prep_queries(pa, st);
+  if (e != cudaSuccess) return e;
+
+  // TMA descriptor over the live part of the corpus: [n_rows][row_elems] bf16, box 64 x 64, 128B swizzle
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.row_elems), static_cast<cuuint64_t>(p.n_rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.row_elems) * 2};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kNB)};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.vectors), gdim, gstride, box,
+                            estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+
+  Args a{};
+  a.q_bf16 = q_bf16; a.q_norm2 = q_norm; a.x_norm2 = p.norms2;
+  a.live = p.live; a.filter = p.filter; a.filter_words = p.filter_words;
+  a.n_rows = p.n_rows; a.row_elems = p.row_elems; a.B = p.B; a.k = p.k; a.cpm = L.cpm; a.partial = part;
+  // lists of CTAs that never see a tile must still read as empty
+  e = cudaMemsetAsync(part, 0xFF, static_cast<size_t>(L.cpm) * p.B * p.k * 8, st);
+  if (e != cudaSuccess) return e;
+  dim3 grid(L.cpm, L.n_mtiles, 1);
+  const bool l2 = (p.space == 0);
+  if (p.k <= 16) e = launch_kl<16>(tmap, a, l2, grid, st);
+  else if (p.k <= 128) e = launch_kl<128>(tmap, a, l2, grid, st);
+  else e = launch_kl<1024>(tmap, a, l2, grid, st);
+  if (e != cudaSuccess) return e;
+  *partial = part;
+  *S = L.cpm;
+  if (launches) *launches += 2;
+  return cudaSuccess;
+}
+
+}  // namespace tensor
+}  // namespace rag

@@ -235,3 +235,123 @@ def test_large_streaming_properties():
         assert np.array_equal(r2[:, :k - 1], rows[:, 1:]) and np.array_equal(d2[:, :k - 1], dists[:, 1:])
     finally:
         st.close()
+
+
+# ------------------------------------------------------------------------------------
+# tensor regime (tcgen05): bf16 stores, queries resident in TMEM
+# ------------------------------------------------------------------------------------
+TENSOR_CASES = [
+    # space, n, dim, B, k
+    ("cosine", 5000, 768, 16, 10),
+    ("cosine", 64, 768, 1, 5),            # a single full tile
+    ("cosine", 37, 64, 3, 10),            # fewer rows than one tile, one K atom
+    ("ip", 4099, 384, 128, 10),           # full query tile, ragged last corpus tile
+    ("l2", 3000, 384, 130, 16),           # two query tiles, register list at its limit
+    ("l2", 2000, 768, 40, 17),            # local-memory list
+    ("cosine", 3000, 200, 9, 100),        # K not a multiple of 64/128 (dim 200)
+    ("cosine", 2500, 72, 300, 3),         # K = 72: second atom mostly out of bounds
+    ("ip", 1500, 8, 5, 7),                # smallest row (one 16-byte chunk)
+    ("cosine", 20000, 768, 1024, 10),     # the headline batch shape on a small corpus
+]
+
+
+@pytest.mark.parametrize("space,n,dim,B,k", TENSOR_CASES)
+def test_tensor_regime_matches_oracle(space, n, dim, B, k):
+    rng = np.random.default_rng(n * 7 + dim + B + k)
+    x = rng.standard_normal((n, dim)).astype(np.float32) if space != "cosine" else unit_rows(n, dim, n)
+    q = rng.standard_normal((B, dim)).astype(np.float32)
+    q[0] = x[n // 2] + 0.01 * rng.standard_normal(dim).astype(np.float32)
+    x, q = round_to_bf16(prepare_corpus(space, x)), round_to_bf16(prepare_corpus(space, q))
+    st = DeviceStore(dim, "bf16", space)
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        assert st.last_query_info()["regime"] == "tensor"
+        check_against_oracle(space, "bf16", stored, q, k, rows, dists, counts, min_recall=0.999)
+        # the two regimes agree with each other bit for bit on rows for cosine/ip
+        # (same products, fp32 accumulation; summation order may differ -> compare through the oracle bar)
+        r2, d2, c2 = st.query(q[: min(B, 16)], k, regime="stream")
+        check_against_oracle(space, "bf16", stored, q[: min(B, 16)], k, r2, d2, c2, min_recall=0.999)
+        assert np.allclose(dists[: min(B, 16)], d2, rtol=1e-5, atol=2e-6)
+    finally:
+        st.close()
+
+
+def test_tensor_regime_masks_tombstones_and_tile_skipping():
+    n, dim, k, B = 6000, 384, 10, 33
+    x = round_to_bf16(unit_rows(n, dim, 21))
+    q = round_to_bf16(unit_rows(B, dim, 22))
+    rng = np.random.default_rng(23)
+    st = DeviceStore(dim, "bf16", "cosine")
+    try:
+        st.upsert(x)
+        live = np.ones(n, bool)
+        dead = np.concatenate([np.arange(640, 1920), rng.choice(n, 200, replace=False)])   # 20 whole tiles + scattered
+        st.delete(dead)
+        live[dead] = False
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        check_against_oracle("cosine", "bf16", x, q, k, rows, dists, counts, valid=live, min_recall=0.999)
+        for sel in (0.5, 0.05, 0.002, 0.0):
+            passing = rng.random(n) < sel
+            st.set_mask(1, passing)
+            rows, dists, counts = st.query(q, k, mask_slot=1, regime="tensor")
+            check_against_oracle("cosine", "bf16", x, q, k, rows, dists, counts, valid=live & passing,
+                                 min_recall=0.999)
+        st.set_mask(2, np.ones(1000, bool))
+        rows, dists, counts = st.query(q, k, mask_slot=2, regime="tensor")
+        short = np.zeros(n, bool)
+        short[:1000] = True
+        check_against_oracle("cosine", "bf16", x, q, k, rows, dists, counts, valid=live & short, min_recall=0.999)
+    finally:
+        st.close()
+
+
+def test_auto_regime_switches_on_batch_size():
+    dim = 128
+    x = round_to_bf16(unit_rows(3000, dim, 1))
+    st = DeviceStore(dim, "bf16", "cosine")
+    f32 = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        f32.upsert(x)
+        st.query(x[:4], 5)
+        assert st.last_query_info()["regime"] == "stream"
+        st.query(x[:64], 5)
+        assert st.last_query_info()["regime"] == "tensor"
+        f32.query(x[:64], 5)                               # fp32 stores stay on the exact fp32 stream kernel
+        assert f32.last_query_info()["regime"] == "stream"
+        with pytest.raises(ValueError):
+            f32.query(x[:4], 5, regime="tensor")
+    finally:
+        st.close()
+        f32.close()
+
+
+def test_tensor_regime_large_properties():
+    """2M x 768 bf16, B = 256: planted neighbours at rank 1, agreement with the
+    stream regime on a query subset, deleting winners promotes runners-up."""
+    n, dim, k, B = 2_000_000, 768, 10, 256
+    rng = np.random.default_rng(77)
+    st = DeviceStore(dim, "bf16", "cosine", capacity_hint=n)
+    try:
+        keep = {}
+        chunk = 250_000
+        for s in range(0, n, chunk):
+            xs = rng.standard_normal((chunk, dim), dtype=np.float32)
+            st.upsert(xs)
+            for j in range(32):
+                r = s + (j * 7919) % chunk
+                keep[r] = xs[r - s].copy()
+        planted = sorted(keep)[:B]
+        q = np.stack([keep[r] + 0.02 * rng.standard_normal(dim).astype(np.float32) for r in planted])
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        assert np.all(counts == k) and rows[:, 0].tolist() == planted
+        assert np.all(np.diff(dists, axis=1) >= 0)
+        r2, d2, _ = st.query(q[:8], k, regime="stream")
+        assert np.array_equal(rows[:8], r2) and np.allclose(dists[:8], d2, rtol=1e-5, atol=2e-6)
+        st.delete(rows[:, 0])
+        r3, d3, _ = st.query(q, k, regime="tensor")
+        assert np.array_equal(r3[:, :k - 1], rows[:, 1:])
+    finally:
+        st.close()
