@@ -354,18 +354,20 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   }
   int launches = 0;
   int S = 0;
+  tensor::Result tres{};
   if (regime == 2) {
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     tensor::Problem p{};
     p.vectors = s->d_vectors; p.norms2 = s->d_norms2; p.n_rows = s->rows; p.row_elems = s->row_elems;
     p.dim = s->dim; p.dtype = s->dtype; p.space = s->space;
     p.live = s->d_live; p.filter = filter; p.filter_words = fwords;
+    p.dense = (filter == nullptr && s->live == s->rows) ? 1 : 0;
     p.queries_raw = d_queries_raw; p.B = B; p.k = k;
     p.scratch = d_tensor; p.sm_count = s->sm_count;
-    const uint64_t* tpartial = nullptr;
-    cudaError_t e = tensor::launch(s->tensor_plan, p, st, &tpartial, &S, &launches);
-    d_partial = const_cast<uint64_t*>(tpartial);
+    cudaError_t e = tensor::launch(s->tensor_plan, p, st, &tres, &launches);
     if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RAG_ECUDA, "tensor-regime launch failed: %s", cudaGetErrorString(e)); }
+    d_partial = const_cast<uint64_t*>(tres.partial);
+    S = tres.S;
     if (timed) CUDA_TRY(cudaEventRecord(c->ev1, st));
   } else {
     PrepArgs pa{};
@@ -389,8 +391,20 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   MergeArgs ma{};
   ma.keys = d_partial; ma.S = S; ma.B = B; ma.k = k; ma.row_base = row_base;
   ma.out_keys = out.keys; ma.out_rows = out.rows; ma.out_dists = out.dists; ma.out_counts = out.counts;
+  const bool refine = (regime == 2 && s->space == RAG_SPACE_L2);
+  if (refine) {   // merge to scratch keys first, then re-score the winners exactly
+    ma.row_base = 0; ma.out_keys = tres.merged; ma.out_rows = nullptr; ma.out_dists = nullptr; ma.out_counts = nullptr;
+  }
   CUDA_TRY(launch_merge(ma, st));
   launches++;
+  if (refine) {
+    RefineArgs ra{};
+    ra.keys = tres.merged; ra.vectors = s->d_vectors; ra.queries = tres.q_f32;
+    ra.dtype = s->dtype; ra.row_elems = s->row_elems; ra.B = B; ra.k = k; ra.row_base = row_base;
+    ra.out_keys = out.keys; ra.out_rows = out.rows; ra.out_dists = out.dists; ra.out_counts = out.counts;
+    CUDA_TRY(launch_refine_l2(ra, st));
+    launches++;
+  }
   s->launches += launches;
   s->last_launches = launches;
   s->last_regime = regime;

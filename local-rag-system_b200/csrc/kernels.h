@@ -46,6 +46,20 @@ struct MergeArgs {
 };
 cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
 
+// exact l2 re-scoring + re-sort of the B x k winners (tensor regime)
+struct RefineArgs {
+  const uint64_t* keys;     // [B][k] merged winners (rows local to the store)
+  const void* vectors;
+  const float* queries;     // [B][row_elems] prepared fp32
+  int dtype, row_elems, B, k;
+  uint32_t row_base;
+  uint64_t* out_keys;
+  int64_t* out_rows;
+  float* out_dists;
+  int32_t* out_counts;
+};
+cudaError_t launch_refine_l2(const RefineArgs& a, cudaStream_t st);
+
 // ---- K1: normalise / convert on upsert ------------------------------------------
 struct UpsertArgs {
   const float* src;         // [n][dim] fp32 (device)

@@ -71,7 +71,71 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs a)
   }
 }
 
+// ---- exact re-scoring of the k winners (tensor regime, l2 space) --------------------
+// The tensor kernel ranks by |q|^2 + |x|^2 - 2 q.x, whose cancellation error grows
+// with the norms.  The k survivors per query are re-scored here with the direct
+// sum((q-x)^2) the stream kernel uses, re-sorted and emitted, so reported distances
+// meet the same tolerance in both regimes.  One CTA per query, one warp per row.
+__global__ void __launch_bounds__(kMergeThreads) refine_l2_kernel(const RefineArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int k = a.k;
+  const int kpad = next_pow2(k);
+  for (int i = threadIdx.x; i < kpad; i += blockDim.x) keys[i] = kEmptyKey;
+  __syncthreads();
+  const float* q = a.queries + static_cast<size_t>(b) * a.row_elems;
+  for (int j = warp; j < k; j += kMergeWarps) {
+    const uint64_t key = a.keys[static_cast<size_t>(b) * k + j];
+    if (key == kEmptyKey) continue;
+    const uint32_t row = key_row(key);
+    float acc = 0.0f;
+    if (a.dtype == 1) {
+      const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.vectors) + static_cast<size_t>(row) * a.row_elems;
+      for (int e = lane; e < a.row_elems; e += 32) { float d = __bfloat162float(x[e]) - q[e]; acc = fmaf(d, d, acc); }
+    } else {
+      const float* x = reinterpret_cast<const float*>(a.vectors) + static_cast<size_t>(row) * a.row_elems;
+      for (int e = lane; e < a.row_elems; e += 32) { float d = x[e] - q[e]; acc = fmaf(d, d, acc); }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) keys[j] = make_key(acc, row);
+  }
+  __syncthreads();
+  block_bitonic_sort(keys, kpad);
+  int cnt = 0;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    uint64_t key = keys[j];
+    const bool valid = key != kEmptyKey;
+    if (valid) {
+      key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+      cnt++;
+    }
+    const size_t o = static_cast<size_t>(b) * k + j;
+    if (a.out_keys) a.out_keys[o] = key;
+    if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
+    if (a.out_dists) a.out_dists[o] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+  }
+  if (a.out_counts) {
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) a.out_counts[b] = total;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_refine_l2(const RefineArgs& a, cudaStream_t st) {
+  if (a.B <= 0 || a.k <= 0) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(next_pow2(a.k)) * sizeof(uint64_t);
+  refine_l2_kernel<<<a.B, kMergeThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.k <= 0 || a.S <= 0) return cudaErrorInvalidValue;

@@ -12,7 +12,8 @@
 //     (tcgen05.mma ... [d_tmem], [a_tmem], b_desc): the queries never touch shared
 //     memory or L2 again, so on-chip traffic is the corpus stream only.
 //   * the corpus streams HBM -> TMA (128B-swizzled boxes of 64 rows x 64 elements)
-//     -> a 12-stage / 192 KB shared-memory ring -> tcgen05.mma as the B operand.
+//     -> a 7-stage x 32 KB = 224 KB shared-memory ring -> tcgen05.mma as the B operand;
+//     tiles a few steps ahead are pulled into L2 with cp.async.bulk.prefetch.tensor.
 //     Every corpus byte is read from HBM once per batch (CTAs serving different
 //     query tiles walk the corpus tiles in the same order, so re-reads hit L2).
 //   * accumulators: 2 x 64 fp32 columns of TMEM (double buffered): while the
@@ -31,6 +32,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -44,10 +47,13 @@ namespace {
 constexpr int kM = 128;              // queries per CTA (MMA M)
 constexpr int kNB = 64;              // corpus rows per tile (MMA N)
 constexpr int kAtomK = 64;           // bf16 elements per 128-byte swizzle atom row
-constexpr int kStageK = 128;         // K elements per pipeline stage (two atoms)
+constexpr int kAtomsPerStage = 4;
+constexpr int kStageK = kAtomK * kAtomsPerStage;      // 256 K elements per pipeline stage
 constexpr int kAtomBytes = kNB * kAtomK * 2;          // 8 KB
-constexpr int kStageBytes = 2 * kAtomBytes;            // 16 KB
-constexpr int kStages = 12;                            // 192 KB in flight per SM
+constexpr int kStageBytes = kAtomsPerStage * kAtomBytes;   // 32 KB
+constexpr int kStages = 7;                             // 224 KB in flight per SM
+constexpr int kPrefetchTiles = 4;                      // L2 prefetch distance, in this CTA's tiles
+constexpr int kMmasPerStage = kStageK / 16;            // 16
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
@@ -79,6 +85,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
+// exactly one lane of the (converged) warp gets true.  Using elect.sync -- rather than
+// `lane == 0` -- lets ptxas keep the TMA / MMA operands in uniform registers; with a
+// plain lane test it wraps every UTCHMMA / UTMALDG in a per-lane "waterfall" loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}" : "+r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -89,6 +109,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(map), "r"(bar), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -115,6 +153,10 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -161,6 +203,8 @@ struct Args {
   int row_elems;
   int B, k;
   int cpm;                       // CTAs per query tile
+  int dense;                     // 1: no filter and no tombstones -> tile masks are computed, not loaded
+  int prefetch;                  // L2 prefetch distance in tiles (0 = off)
   uint64_t* partial;             // [cpm][B][k]
 };
 
@@ -200,7 +244,11 @@ struct TopList {
   }
 };
 
-template <int KL, bool L2>
+// CL = CTAs per cluster.  The CL CTAs of a cluster serve CL different query tiles and walk
+// the same corpus tiles; each loads 1/CL of every tile and TMA-multicasts it to all of
+// them, so L2 -> SM traffic per CTA drops by CL (L2 bandwidth ~ HBM bandwidth on this chip,
+// and it is what bounds the unicast version at ~0.9 PFLOP/s).
+template <int KL, bool L2, int CL>
 __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -225,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
     for (int b = 0; b < 2; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
     fence_barrier_init();
   }
@@ -235,16 +283,44 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // peers' barriers exist before anyone multicasts into them
   tc_fence_after();
+  const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(kMaxKCols);   // accumulators after the A columns
 
-  auto tile_mask = [&](int64_t t, uint32_t& w0, uint32_t& w1) {
-    w0 = __ldg(a.live + 2 * t);
-    w1 = __ldg(a.live + 2 * t + 1);
-    if (a.filter != nullptr) {
-      w0 &= (2 * t < a.filter_words) ? __ldg(a.filter + 2 * t) : 0u;
-      w1 &= (2 * t + 1 < a.filter_words) ? __ldg(a.filter + 2 * t + 1) : 0u;
+  // Walks this CTA's corpus tiles (cj, cj + cpm, ...) and yields the ones with at least one
+  // live & filter-passing row.  Mask words of the NEXT tile are requested one step ahead so
+  // that no role ever stalls on a dependent global load; dense stores compute them instead.
+  struct TileWalker {
+    const Args& a;
+    int64_t t, n_tiles;
+    uint32_t p0, p1;      // prefetched mask words of tile t
+    __device__ __forceinline__ void fetch() {
+      if (t >= n_tiles) { p0 = p1 = 0u; return; }
+      if (a.dense) {
+        const int64_t left = a.n_rows - t * kNB;
+        p0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        p1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
+        return;
+      }
+      p0 = __ldg(a.live + 2 * t);
+      p1 = __ldg(a.live + 2 * t + 1);
+      if (a.filter != nullptr) {
+        p0 &= (2 * t < a.filter_words) ? __ldg(a.filter + 2 * t) : 0u;
+        p1 &= (2 * t + 1 < a.filter_words) ? __ldg(a.filter + 2 * t + 1) : 0u;
+      }
+    }
+    __device__ __forceinline__ TileWalker(const Args& a_, int64_t t0, int64_t n) : a(a_), t(t0), n_tiles(n) { fetch(); }
+    __device__ __forceinline__ bool next(int64_t& tile, uint32_t& w0, uint32_t& w1) {
+      while (t < n_tiles) {
+        tile = t; w0 = p0; w1 = p1;
+        t += a.cpm;
+        fetch();
+        if ((w0 | w1) != 0u) return true;
+      }
+      return false;
     }
   };
 
@@ -279,10 +355,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     const float qn = (L2 && q_valid) ? a.q_norm2[b] : 0.0f;
 
     uint32_t it = 0;
-    for (int64_t t = cj; t < n_tiles; t += a.cpm) {
-      uint32_t w0, w1;
-      tile_mask(t, w0, w1);
-      if ((w0 | w1) == 0u) continue;                 // tile skipped by every role
+    TileWalker walk(a, cj, n_tiles);
+    int64_t t;
+    uint32_t w0, w1;
+    while (walk.next(t, w0, w1)) {                   // tiles with no passing row are skipped by every role
       const int buf = it & 1;
       const uint32_t par = (it >> 1) & 1;
       ++it;
@@ -347,24 +423,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     }
     tc_fence_before();
   } else if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      for (int64_t t = cj; t < n_tiles; t += a.cpm) {
-        uint32_t w0, w1;
-        tile_mask(t, w0, w1);
-        if ((w0 | w1) == 0u) continue;
-        const int row0 = static_cast<int>(t * kNB);
-        for (int ks = 0; ks < n_stages_per_tile; ++ks) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const int k0 = ks * kStageK;
-          const bool two = (k0 + kAtomK) < a.row_elems;
-          mbar_arrive_expect_tx(full_bar(s), two ? kStageBytes : kAtomBytes);
-          const uint32_t dst = base + s * kStageBytes;
-          tma_load_2d(dst, &tmap, full_bar(s), k0, row0);
-          if (two) tma_load_2d(dst + kAtomBytes, &tmap, full_bar(s), k0 + kAtomK, row0);
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+    // ================= TMA producer (whole warp walks the loop, one elected lane issues) =========
+    uint32_t s = 0, ph = 0;
+    TileWalker walk(a, cj, n_tiles);
+    int64_t t;
+    uint32_t w0, w1;
+    while (walk.next(t, w0, w1)) {
+      const int row0 = static_cast<int>(t * kNB);
+      // pull this CTA's slice of a tile kPrefetchTiles steps ahead into L2 (hides DRAM latency
+      // when the CTAs sharing a corpus tile have drifted apart and it is no longer L2-resident)
+      {
+        const int64_t tp = t + static_cast<int64_t>(a.prefetch) * a.cpm;
+        if (a.prefetch > 0 && tp < n_tiles && elect_one()) {
+          const int rp = static_cast<int>(tp * kNB) + static_cast<int>(crank) * (kNB / CL);
+          for (int kc = 0; kc < a.row_elems; kc += kAtomK) tma_prefetch_l2_2d(&tmap, kc, rp);
         }
+        __syncwarp();
+      }
+      for (int ks = 0; ks < n_stages_per_tile; ++ks) {
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int k0 = ks * kStageK;
+        int atoms = (a.row_elems - k0 + kAtomK - 1) / kAtomK;       // atoms that hold real columns
+        atoms = atoms > kAtomsPerStage ? kAtomsPerStage : atoms;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(atoms) * kAtomBytes);   // bytes from all CL loaders
+          const uint32_t dst = base + s * kStageBytes + crank * (kAtomBytes / CL);
+          const int r0 = row0 + static_cast<int>(crank) * (kNB / CL);
+#pragma unroll
+          for (int at = 0; at < kAtomsPerStage; ++at) {
+            if (at < atoms) {
+              if constexpr (CL == 1) tma_load_2d(dst + at * kAtomBytes, &tmap, full_bar(s), k0 + at * kAtomK, r0);
+              else tma_load_2d_mc(dst + at * kAtomBytes, &tmap, full_bar(s), k0 + at * kAtomK, r0, kMcMask);
+            }
+          }
+        }
+        __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
@@ -372,31 +466,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     asm volatile("bar.sync 1, 160;" ::: "memory");   // wait for the A operand
     tc_fence_after();
     uint32_t s = 0, ph = 0, it = 0;
-    for (int64_t t = cj; t < n_tiles; t += a.cpm) {
-      uint32_t w0, w1;
-      tile_mask(t, w0, w1);
-      if ((w0 | w1) == 0u) continue;
+    const uint64_t desc0 = make_b_desc(base);        // descriptor of stage 0, atom 0, k = 0
+    TileWalker walk(a, cj, n_tiles);
+    int64_t t;
+    uint32_t w0, w1;
+    while (walk.next(t, w0, w1)) {
       const int buf = it & 1;
       const uint32_t par = (it >> 1) & 1;
       ++it;
       mbar_wait(acce_bar(buf), par ^ 1u);           // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_tmem = tmem_acc + static_cast<uint32_t>(buf * kAccCols);
-      int kk = 0;
       for (int ks = 0; ks < n_stages_per_tile; ++ks) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t stage = base + s * kStageBytes;
+        if (elect_one()) {
+          // descriptors advance by plain adds: stage (32 KB), atom (8 KB), k-step inside an atom (32 B), in 16-byte units
+          const uint64_t dstage = desc0 + static_cast<uint64_t>((s * kStageBytes) >> 4);
+          const uint32_t a0 = tmem_base + static_cast<uint32_t>(ks * kMmasPerStage * 8);
+          const int left = k_steps - ks * kMmasPerStage;
+          if (left >= kMmasPerStage) {
 #pragma unroll
-          for (int j = 0; j < kStageK / 16; ++j) {
-            if (kk < k_steps) {
-              const uint32_t b_addr = stage + (j >> 2) * kAtomBytes + (j & 3) * 32;
-              umma_ts(d_tmem, tmem_base + static_cast<uint32_t>(kk * 8), make_b_desc(b_addr), kIdesc, kk > 0 ? 1u : 0u);
-            }
-            ++kk;
+            for (int j = 0; j < kMmasPerStage; ++j)
+              umma_ts(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4), kIdesc,
+                      (j > 0) ? 1u : (ks > 0 ? 1u : 0u));
+          } else {
+#pragma unroll
+            for (int j = 0; j < kMmasPerStage; ++j)
+              if (j < left)
+                umma_ts(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4), kIdesc,
+                        (j > 0) ? 1u : (ks > 0 ? 1u : 0u));
           }
-          umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+          if constexpr (CL == 1) umma_commit(empty_bar(s));   // stage reusable once these MMAs retire
+          else umma_commit_mc(empty_bar(s), kMcMask);          // ... in every CTA that loads into it
           if (ks == n_stages_per_tile - 1) umma_commit(accf_bar(buf));
         }
         __syncwarp();
@@ -407,6 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   }
 
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // no peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -434,13 +537,16 @@ EncodeTiledFn get_encode() {
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
-  int n_mtiles, cpm;
-  size_t off_qbf16, off_qnorm, off_qf32, off_partial, total;
+  int n_mtiles, cpm, cl;
+  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_merged, total;
 };
 
 Layout make_layout(int row_elems, int B, int k, int sm_count) {
   Layout L{};
   L.n_mtiles = (B + kM - 1) / kM;
+  L.cl = (L.n_mtiles >= 2) ? 2 : 1;
+  if (const char* e = getenv("RAG_B200_TENSOR_CL")) { if (atoi(e) == 1) L.cl = 1; }
+  L.n_mtiles = (L.n_mtiles + L.cl - 1) / L.cl * L.cl;   // pad with idle query tiles to whole clusters
   L.cpm = sm_count / L.n_mtiles;
   if (L.cpm < 1) L.cpm = 1;
   size_t off = 0;
@@ -448,23 +554,35 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.off_qnorm = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);
   L.off_qf32 = off;  off += align256(static_cast<size_t>(B) * row_elems * 4);
   L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
+  L.off_merged = off; off += align256(static_cast<size_t>(B) * k * 8);
   L.total = off;
   return L;
 }
 
+template <int KL, bool L2, int CL>
+cudaError_t launch_one(const CUtensorMap& tmap, const Args& a, dim3 grid, cudaStream_t st) {
+  auto kern = gemm_topk_kernel<KL, L2, CL>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CL;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmap, a);
+}
+
 template <int KL>
-cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, dim3 grid, cudaStream_t st) {
-  cudaError_t e;
-  if (l2) {
-    e = cudaFuncSetAttribute(gemm_topk_kernel<KL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    gemm_topk_kernel<KL, true><<<grid, kThreads, kSmemBytes, st>>>(tmap, a);
-  } else {
-    e = cudaFuncSetAttribute(gemm_topk_kernel<KL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return e;
-    gemm_topk_kernel<KL, false><<<grid, kThreads, kSmemBytes, st>>>(tmap, a);
-  }
-  return cudaGetLastError();
+cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int cl, dim3 grid, cudaStream_t st) {
+  if (cl == 2) return l2 ? launch_one<KL, true, 2>(tmap, a, grid, st) : launch_one<KL, false, 2>(tmap, a, grid, st);
+  return l2 ? launch_one<KL, true, 1>(tmap, a, grid, st) : launch_one<KL, false, 1>(tmap, a, grid, st);
 }
 
 }  // namespace
@@ -486,7 +604,7 @@ Plan* create_plan() { return new Plan(); }
 void destroy_plan(Plan* p) { delete p; }
 void invalidate(Plan*) {}
 
-cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, const uint64_t** partial, int* S, int* launches) {
+cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* launches) {
   if (!supported(p.dtype, p.row_elems, p.k, p.space)) return cudaErrorNotSupported;
   const Layout L = make_layout(p.row_elems, p.B, p.k, p.sm_count);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(p.scratch + L.off_qbf16);
@@ -508,7 +626,7 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, const uint64_t** pa
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.row_elems), static_cast<cuuint64_t>(p.n_rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.row_elems) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kNB)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kNB / L.cl)};
   const cuuint32_t estride[2] = {1, 1};
   CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.vectors), gdim, gstride, box,
                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -519,17 +637,22 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, const uint64_t** pa
   a.q_bf16 = q_bf16; a.q_norm2 = q_norm; a.x_norm2 = p.norms2;
   a.live = p.live; a.filter = p.filter; a.filter_words = p.filter_words;
   a.n_rows = p.n_rows; a.row_elems = p.row_elems; a.B = p.B; a.k = p.k; a.cpm = L.cpm; a.partial = part;
+  a.dense = p.dense;
+  a.prefetch = 0;
+  if (const char* e = getenv("RAG_B200_TENSOR_PF")) a.prefetch = atoi(e);
   // lists of CTAs that never see a tile must still read as empty
   e = cudaMemsetAsync(part, 0xFF, static_cast<size_t>(L.cpm) * p.B * p.k * 8, st);
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm, L.n_mtiles, 1);
   const bool l2 = (p.space == 0);
-  if (p.k <= 16) e = launch_kl<16>(tmap, a, l2, grid, st);
-  else if (p.k <= 128) e = launch_kl<128>(tmap, a, l2, grid, st);
-  else e = launch_kl<1024>(tmap, a, l2, grid, st);
+  if (p.k <= 16) e = launch_kl<16>(tmap, a, l2, L.cl, grid, st);
+  else if (p.k <= 128) e = launch_kl<128>(tmap, a, l2, L.cl, grid, st);
+  else e = launch_kl<1024>(tmap, a, l2, L.cl, grid, st);
   if (e != cudaSuccess) return e;
-  *partial = part;
-  *S = L.cpm;
+  out->partial = part;
+  out->S = L.cpm;
+  out->q_f32 = q_f32;
+  out->merged = reinterpret_cast<uint64_t*>(p.scratch + L.off_merged);
   if (launches) *launches += 2;
   return cudaSuccess;
 }

@@ -20,6 +20,7 @@ struct Problem {
   const uint32_t* live;
   const uint32_t* filter;
   int64_t filter_words;
+  int dense;                // no filter and every row below n_rows is live
   const float* queries_raw; // [B][dim] fp32, unprepared
   int B, k;
   unsigned char* scratch;   // scratch_bytes() bytes
@@ -31,9 +32,14 @@ size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count);
 Plan* create_plan();
 void destroy_plan(Plan* p);
 void invalidate(Plan* p);     // corpus pointer / capacity changed
-// Runs prep + contraction + fused select.  On success *partial holds S ascending
-// candidate lists per query laid out [S][B][k] inside `scratch`.
-cudaError_t launch(Plan* plan, const Problem& p, cudaStream_t st, const uint64_t** partial, int* S, int* launches);
+struct Result {
+  const uint64_t* partial;  // [S][B][k] ascending candidate lists per query (inside `scratch`)
+  int S;
+  const float* q_f32;       // [B][row_elems] prepared queries (for the l2 refinement)
+  uint64_t* merged;         // [B][k] scratch for the merged keys before refinement
+};
+// Runs prep + contraction + fused select.
+cudaError_t launch(Plan* plan, const Problem& p, cudaStream_t st, Result* out, int* launches);
 
 }  // namespace tensor
 }  // namespace rag
