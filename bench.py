@@ -242,7 +242,7 @@ def main():
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[K])
     per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
-    launches = store.kernel_launches() - launches0 + K          # + the cross-shard merge kernel per step
+    launches = store.kernel_launches() - launches0 + (K if world > 1 else 0)   # + the cross-shard merge kernel per step
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

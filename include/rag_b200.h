@@ -147,9 +147,14 @@ RAG_API int rag_store_query(rag_store* s, int B, const float* queries, int k, in
  * pointers; nothing is copied to the host.  `row_base` (this shard's first
  * global row) is added to the row field of every emitted key, so keys from
  * different shards merge by plain 64-bit comparison in exactly the order a
- * single store would produce.  Global rows must stay below 2^32.             */
+ * single store would produce.  Global rows must stay below 2^32.
+ * out_rows_dev / out_dists_dev / out_counts_dev (B x k, B x k, B; each may be
+ * NULL) additionally receive the decoded result -- a single-shard caller needs
+ * no merge step.  At least one of out_keys_dev / out_rows_dev must be given.   */
 RAG_API int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, int mask_slot,
-                        int flags, uint32_t row_base, uint64_t* out_keys_dev, void* stream);
+                        int flags, uint32_t row_base, uint64_t* out_keys_dev,
+                        int64_t* out_rows_dev, float* out_dists_dev, int32_t* out_counts_dev,
+                        void* stream);
 
 /* Cross-shard merge (after the NCCL all-gather of per-shard candidates):
  * keys_dev is G x B x k (each list ascending).  Writes B x k global rows /

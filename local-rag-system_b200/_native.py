@@ -53,7 +53,7 @@ SIGNATURES = {
     "rag_store_set_mask": (C.c_int, [_p, C.c_int, _p, C.c_int64]),
     "rag_store_clear_mask": (C.c_int, [_p, C.c_int]),
     "rag_store_query": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
-    "rag_store_query_dev": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p]),
+    "rag_store_query_dev": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p, _p, _p]),
     "rag_merge_keys_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),
     "rag_key_pack": (C.c_uint64, [C.c_float, C.c_uint32]),
     "rag_key_dist": (C.c_float, [C.c_uint64]),

@@ -7,6 +7,7 @@
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -330,10 +331,12 @@ struct SearchOut {
   int32_t* counts = nullptr;
 };
 
+// stream-regime scratch: prepared queries | per-CTA partial lists [grid_x][B][k] | tickets [B]
 size_t search_scratch_bytes(const rag_store* s, int B, int k, int grid_x) {
   size_t q = align_up((size_t)B * s->row_elems * sizeof(float), 256);
   size_t part = align_up((size_t)grid_x * B * k * sizeof(uint64_t), 256);
-  return q + part + tensor::scratch_bytes(s->dtype, s->row_elems, B, k, s->sm_count);
+  size_t st = align_up((size_t)B * sizeof(int), 256);
+  return q + part + st + tensor::scratch_bytes(s->dtype, s->row_elems, B, k, s->sm_count);
 }
 
 int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
@@ -344,6 +347,8 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   size_t off = align_up((size_t)B * s->row_elems * sizeof(float), 256);
   uint64_t* d_partial = reinterpret_cast<uint64_t*>(scratch + off);
   off += align_up((size_t)grid_x * B * k * sizeof(uint64_t), 256);
+  int* d_state = reinterpret_cast<int*>(scratch + off);      // tickets [B]
+  off += align_up((size_t)B * sizeof(int), 256);
   unsigned char* d_tensor = scratch + off;
 
   const uint32_t* filter = nullptr;
@@ -375,6 +380,8 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
     pa.normalise = (s->space == RAG_SPACE_COSINE);
     pa.round_bf16 = (s->dtype == RAG_DTYPE_BF16);
     pa.q_f32 = d_q; pa.q_bf16 = nullptr; pa.q_norm2 = nullptr;
+    pa.init_keys = nullptr; pa.init_keys_n = 0;
+    pa.init_zero = d_state; pa.init_zero_n = (int64_t)B;
     CUDA_TRY(launch_prep_queries(pa, st));
     launches++;
     ScanArgs sa{};
@@ -382,10 +389,20 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
     sa.cpr = (int)(s->row_bytes / 16);
     sa.n_rows = s->rows; sa.live = s->d_live; sa.filter = filter; sa.filter_words = fwords;
     sa.queries = d_q; sa.B = B; sa.k = k; sa.l2 = (s->space == RAG_SPACE_L2);
-    sa.partial = d_partial; sa.grid_x = grid_x;
+    sa.grid_x = grid_x;
+    static const bool fused = !(getenv("RAG_B200_FUSED_MERGE") && atoi(getenv("RAG_B200_FUSED_MERGE")) == 0);
+    sa.partial = d_partial; sa.done = fused ? reinterpret_cast<unsigned int*>(d_state) : nullptr; sa.merge_keys_cap = 0;
+    sa.row_base = row_base;
+    sa.out_keys = out.keys; sa.out_rows = out.rows; sa.out_dists = out.dists; sa.out_counts = out.counts;
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     CUDA_TRY(launch_scan_stream(sa, s->sm_count, st, &launches));
     if (timed) CUDA_TRY(cudaEventRecord(c->ev1, st));
+    if (fused) {   // the scan kernel merged across CTAs and emitted the result itself
+      s->launches += launches;
+      s->last_launches = launches;
+      s->last_regime = regime;
+      return RAG_OK;
+    }
     S = grid_x;
   }
   MergeArgs ma{};
@@ -716,16 +733,20 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
 }
 
 int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, int mask_slot, int flags,
-                        uint32_t row_base, uint64_t* out_keys_dev, void* stream) {
+                        uint32_t row_base, uint64_t* out_keys_dev, int64_t* out_rows_dev, float* out_dists_dev,
+                        int32_t* out_counts_dev, void* stream) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");
   RdLock g(&s->lock);
   int rc = check_query_args(s, B, queries_dev, k, mask_slot);
   if (rc != RAG_OK) return rc;
-  if (!out_keys_dev) return fail(RAG_EINVAL, "out_keys_dev is NULL");
+  if (!out_keys_dev && !out_rows_dev) return fail(RAG_EINVAL, "out_keys_dev and out_rows_dev are both NULL");
   CUDA_TRY(cudaSetDevice(s->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (s->live == 0) {
-    CUDA_TRY(cudaMemsetAsync(out_keys_dev, 0xFF, (size_t)B * k * sizeof(uint64_t), st));
+    if (out_keys_dev) CUDA_TRY(cudaMemsetAsync(out_keys_dev, 0xFF, (size_t)B * k * sizeof(uint64_t), st));
+    if (out_rows_dev) CUDA_TRY(cudaMemsetAsync(out_rows_dev, 0xFF, (size_t)B * k * sizeof(int64_t), st));   // -1
+    if (out_dists_dev) CUDA_TRY(cudaMemsetAsync(out_dists_dev, 0x7F, (size_t)B * k * sizeof(float), st));     // large, not inf
+    if (out_counts_dev) CUDA_TRY(cudaMemsetAsync(out_counts_dev, 0, (size_t)B * sizeof(int32_t), st));
     return RAG_OK;
   }
   if (B > batch_limit(s, k)) return fail(RAG_EINVAL, "batch %d too large for one asynchronous call (limit %d)", B, batch_limit(s, k));
@@ -750,6 +771,9 @@ int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, in
   if (rc != RAG_OK) return rc;
   SearchOut so{};
   so.keys = out_keys_dev;
+  so.rows = out_rows_dev;
+  so.dists = out_dists_dev;
+  so.counts = out_counts_dev;
   return search_device(s, c, c->d_buf, B, queries_dev, k, mask_slot, regime, row_base, so, false);
 }
 

@@ -24,8 +24,17 @@ struct ScanArgs {
   int B;
   int k;
   int l2;                   // 1: d = sum((q-x)^2), 0: d = 1 - q.x
-  uint64_t* partial;        // [grid_x][B][k] keys (ascending per list)
   int grid_x;
+  // fused cross-CTA merge: every CTA publishes its sorted top-k, the LAST CTA of a query
+  // group to finish (atomic ticket) merges all of them and emits the final result.
+  uint64_t* partial;        // [grid_x][B][k] keys (ascending per list)
+  unsigned int* done;       // [ceil(B / QB)] tickets, zero-initialised (prep kernel)
+  int merge_keys_cap;       // keys of dynamic shared memory usable by the final in-smem sort (power of two)
+  uint32_t row_base;        // added to emitted rows (multi-GPU: this shard's first global row)
+  uint64_t* out_keys;       // [B][k] or nullptr
+  int64_t* out_rows;        // [B][k] or nullptr
+  float* out_dists;         // [B][k] or nullptr
+  int32_t* out_counts;      // [B]    or nullptr
 };
 // picks QB (queries per pass) and the kernel instantiation; returns cudaError_t
 cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st, int* launches);
@@ -33,6 +42,8 @@ cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st,
 int scan_stream_grid_x(int sm_count, int64_t n_rows);
 // max queries per launch the stream kernel handles in one corpus pass
 int scan_stream_max_qb(int dtype, int row_elems, int k);
+// number of query groups (grid.y) the launcher will use; `done` needs that many tickets
+int scan_stream_groups(int B, int dtype, int row_elems, int k);
 
 // ---- K4b/K6: merge S sorted candidate lists per query ------------------------
 struct MergeArgs {
@@ -85,6 +96,11 @@ struct PrepArgs {
   float* q_f32;             // [B][row_elems]
   __nv_bfloat16* q_bf16;    // [Bpad][row_elems] or nullptr (rows >= B zero-filled by caller)
   float* q_norm2;           // [B] or nullptr
+  // optional initialisation of the scan kernel's merge state (done here to save launches)
+  uint64_t* init_keys;      // filled with kEmptyKey (init_keys_n entries) or nullptr
+  int64_t init_keys_n;
+  int* init_zero;           // zero-filled (init_zero_n ints) or nullptr
+  int64_t init_zero_n;
 };
 cudaError_t launch_prep_queries(const PrepArgs& a, cudaStream_t st);
 

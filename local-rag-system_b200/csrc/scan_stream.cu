@@ -214,8 +214,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     }
   }
 
-  // ---- CTA merge: sort each query's 8 warp lists together, emit the first k -------
+  // ---- CTA merge: sort each query's 8 warp lists together, publish the first k -----------------
   __syncthreads();
+  __shared__ int s_flag;
+  __shared__ int s_total;
 #pragma unroll 1
   for (int qb = 0; qb < QB; ++qb) {
     const int b = b0 + qb;
@@ -225,11 +227,163 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     uint64_t* out = a.partial + (static_cast<size_t>(blockIdx.x) * a.B + b) * k;
     for (int j = threadIdx.x; j < k; j += blockDim.x) out[j] = region[j];
   }
+  // ---- ticket: the last CTA of this query group merges every CTA's list and emits -------------
+  if (a.done == nullptr) return;      // unfused mode: a separate merge kernel follows
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(a.done + blockIdx.y, 1u);
+    s_flag = (prev == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_flag) return;
+  __threadfence();
+
+  const int S = gridDim.x;
+  const int total = S * k;
+  uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw);      // queries / lists are dead now
+#pragma unroll 1
+  for (int qb = 0; qb < QB; ++qb) {
+    const int b = b0 + qb;
+    if (b >= a.B) break;
+    uint64_t* sorted;
+    __syncthreads();
+    if (k <= 64 && S <= 2 * static_cast<int>(blockDim.x)) {
+      // k-way merge by k rounds of block-wide min over the heads of the S sorted lists.
+      // Thread t owns lists t and t + 256; each keeps its current head and the next key in
+      // registers, so a round costs two barriers (~0.1 us) and no memory latency unless the
+      // same list wins twice in a row.  ~1-2 us for 296 lists x k = 10 (a bitonic sort of the
+      // same candidates needs 55 barrier-separated stages per 1024 keys).
+      uint64_t cur[2], nxt[2];
+      int pos[2];
+      const uint64_t* lst[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int s = threadIdx.x + u * static_cast<int>(blockDim.x);
+        lst[u] = a.partial + (static_cast<size_t>(s < S ? s : 0) * a.B + b) * k;
+        pos[u] = 0;
+        cur[u] = (s < S) ? __ldcg(lst[u]) : kEmptyKey;
+        nxt[u] = (s < S && k > 1) ? __ldcg(lst[u] + 1) : kEmptyKey;
+      }
+      uint64_t* wmin = pool;                 // [8] per-warp minima
+      uint64_t* res = pool + 8;              // [k] result
+      for (int r = 0; r < k; ++r) {
+        uint64_t m = cur[0] < cur[1] ? cur[0] : cur[1];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const uint64_t o = shfl_u64(m, lane ^ off);
+          m = o < m ? o : m;
+        }
+        if (lane == 0) wmin[warp] = m;
+        __syncthreads();
+        uint64_t w = wmin[0];
+#pragma unroll
+        for (int i = 1; i < kScanWarps; ++i) w = wmin[i] < w ? wmin[i] : w;
+        if (threadIdx.x == 0) res[r] = w;
+        if (w != kEmptyKey) {                // keys are unique: exactly one list head equals w
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (cur[u] == w) {
+              cur[u] = nxt[u];
+              pos[u]++;
+              nxt[u] = (pos[u] + 1 < k) ? __ldcg(lst[u] + pos[u] + 1) : kEmptyKey;
+            }
+          }
+        }
+        __syncthreads();
+      }
+      sorted = res;
+    } else if (2 * kpad <= a.merge_keys_cap) {
+      // rounds of: keep the best k so far in pool[0..k), append the next cap-k candidates,
+      // sort the pool.  The pool is kept small (8 KB) on purpose: a larger dynamic
+      // shared-memory request shrinks L1 for every CTA and costs the scan ~4% of HBM bandwidth.
+      const int n = a.merge_keys_cap;
+      const int take = n - k;
+      for (int i = threadIdx.x; i < k; i += blockDim.x) pool[i] = kEmptyKey;
+      for (int pos = 0; pos < total; pos += take) {
+        uint64_t tmp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {        // cap <= 1024 keys: at most 4 candidates per thread per round
+          const int i = threadIdx.x + u * static_cast<int>(blockDim.x);
+          const int c = pos + i;
+          tmp[u] = kEmptyKey;
+          if (i < take && c < total) {
+            const int s = c / k, j = c - s * k;
+            tmp[u] = __ldcg(a.partial + (static_cast<size_t>(s) * a.B + b) * k + j);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = threadIdx.x + u * static_cast<int>(blockDim.x);
+          if (i < take) pool[k + i] = tmp[u];
+        }
+        __syncthreads();
+        block_bitonic_sort(pool, n);
+      }
+      sorted = pool;
+    } else {
+      // large k: per-warp running lists with early exit over the (sorted) source lists
+      for (int i = threadIdx.x; i < kScanWarps * kpad; i += blockDim.x) pool[i] = kEmptyKey;
+      __syncthreads();
+      uint64_t* L = pool + static_cast<size_t>(warp) * kpad;
+      for (int s = warp; s < S; s += kScanWarps) {
+        const uint64_t* src = a.partial + (static_cast<size_t>(s) * a.B + b) * k;
+        bool fin = false;
+        for (int j0 = 0; j0 < k && !fin; j0 += 32) {
+          const int j = j0 + lane;
+          const uint64_t cand = (j < k) ? __ldcg(src + j) : kEmptyKey;
+          uint32_t bal = __ballot_sync(0xffffffffu, cand < L[k - 1]);
+          if (bal != 0xffffffffu) fin = true;
+          while (bal) {
+            const int sl = __ffs(bal) - 1;
+            bal &= (bal - 1);
+            const uint64_t ck = shfl_u64(cand, sl);
+            if (ck < L[k - 1]) warp_list_insert(L, k, ck, lane);
+            else bal = 0;
+          }
+        }
+      }
+      __syncthreads();
+      block_bitonic_sort(pool, kScanWarps * kpad);
+      sorted = pool;
+    }
+    int cnt = 0;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      uint64_t key = sorted[j];
+      const bool valid = key != kEmptyKey;
+      if (valid) {
+        key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+        cnt++;
+      }
+      const size_t o = static_cast<size_t>(b) * k + j;
+      if (a.out_keys) a.out_keys[o] = key;
+      if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
+      if (a.out_dists) a.out_dists[o] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+    }
+    if (a.out_counts) {           // block-wide sum of the valid entries
+      if (threadIdx.x == 0) s_total = 0;
+      __syncthreads();
+      if (cnt) atomicAdd(&s_total, cnt);
+      __syncthreads();
+      if (threadIdx.x == 0) a.out_counts[b] = s_total;
+    }
+  }
 }
 
 size_t scan_smem_bytes(int QB, int row_elems, int k) {
   return static_cast<size_t>(QB) * row_elems * sizeof(float) +
          static_cast<size_t>(QB) * kScanWarps * next_pow2(k) * sizeof(uint64_t);
+}
+
+// dynamic shared memory: the scan's own needs, or 8 KB if that is more (pool of the final merge)
+size_t scan_total_smem(int QB, int row_elems, int k, int grid_x, int* merge_cap) {
+  (void)grid_x;
+  size_t need = scan_smem_bytes(QB, row_elems, k);
+  if (need < 8 * 1024) need = 8 * 1024;
+  int cap = 1;
+  while (static_cast<size_t>(cap) * 2 * sizeof(uint64_t) <= need && cap < 1024) cap <<= 1;
+  *merge_cap = cap;
+  return need;
 }
 
 template <bool BF16, int QB, int NJ, int R>
@@ -275,6 +429,13 @@ int scan_stream_grid_x(int sm_count, int64_t n_rows) {
   return static_cast<int>(g);
 }
 
+int scan_stream_groups(int B, int dtype, int row_elems, int k) {
+  const int max_qb = scan_stream_max_qb(dtype, row_elems, k);
+  int QB = 1;
+  while (QB < B && QB < max_qb) QB <<= 1;
+  return (B + QB - 1) / QB;
+}
+
 int scan_stream_max_qb(int dtype, int row_elems, int k) {
   // shared memory per CTA must allow 2 CTAs/SM: keep it under ~100 KB
   const size_t budget = 100 * 1024;
@@ -291,14 +452,15 @@ cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st,
   while (QB < a.B && QB < max_qb) QB <<= 1;
   if (scan_smem_bytes(QB, a.row_elems, a.k) > 200 * 1024) return cudaErrorInvalidValue;
   dim3 grid(a.grid_x, (a.B + QB - 1) / QB, 1);
-  const size_t smem = scan_smem_bytes(QB, a.row_elems, a.k);
+  ScanArgs aa = a;
+  const size_t smem = scan_total_smem(QB, a.row_elems, a.k, a.grid_x, &aa.merge_keys_cap);
   const bool bf16 = (a.dtype == 1);
   cudaError_t e = cudaErrorInvalidValue;
   switch (QB) {
-    case 1: e = bf16 ? launch_qb<true, 1>(a, grid, smem, st) : launch_qb<false, 1>(a, grid, smem, st); break;
-    case 2: e = bf16 ? launch_qb<true, 2>(a, grid, smem, st) : launch_qb<false, 2>(a, grid, smem, st); break;
-    case 4: e = bf16 ? launch_qb<true, 4>(a, grid, smem, st) : launch_qb<false, 4>(a, grid, smem, st); break;
-    case 8: e = bf16 ? launch_qb<true, 8>(a, grid, smem, st) : launch_qb<false, 8>(a, grid, smem, st); break;
+    case 1: e = bf16 ? launch_qb<true, 1>(aa, grid, smem, st) : launch_qb<false, 1>(aa, grid, smem, st); break;
+    case 2: e = bf16 ? launch_qb<true, 2>(aa, grid, smem, st) : launch_qb<false, 2>(aa, grid, smem, st); break;
+    case 4: e = bf16 ? launch_qb<true, 4>(aa, grid, smem, st) : launch_qb<false, 4>(aa, grid, smem, st); break;
+    case 8: e = bf16 ? launch_qb<true, 8>(aa, grid, smem, st) : launch_qb<false, 8>(aa, grid, smem, st); break;
     default: break;
   }
   if (launches) *launches += 1;

@@ -68,6 +68,12 @@ __global__ void clear_live_kernel(uint32_t* live, const int64_t* rows, int64_t n
 
 __global__ void __launch_bounds__(kThreads) prep_queries_kernel(const PrepArgs a) {
   const int lane = threadIdx.x & 31;
+  {   // merge-state initialisation for the scan kernel that follows on the stream
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    if (a.init_keys) for (int64_t i = tid; i < a.init_keys_n; i += nth) a.init_keys[i] = kEmptyKey;
+    if (a.init_zero) for (int64_t i = tid; i < a.init_zero_n; i += nth) a.init_zero[i] = 0;
+  }
   const int b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (b >= a.B) return;
   const float* src = a.src + static_cast<size_t>(b) * a.dim;

@@ -134,13 +134,16 @@ class DeviceStore:
                                           _ptr(rows), _ptr(dists), _ptr(counts)))
         return rows, dists, counts
 
-    def query_device(self, queries_ptr: int, B: int, k: int, out_keys_ptr: int, stream: int = 0,
-                     mask_slot: int = -1, row_base: int = 0, regime: str = "auto"):
-        """Asynchronous shard-local search on device buffers (multi-GPU path)."""
+    def query_device(self, queries_ptr: int, B: int, k: int, out_keys_ptr: int = 0, stream: int = 0,
+                     mask_slot: int = -1, row_base: int = 0, regime: str = "auto",
+                     out_rows_ptr: int = 0, out_dists_ptr: int = 0, out_counts_ptr: int = 0):
+        """Asynchronous shard-local search on device buffers (multi-GPU path).  Emits
+        candidate keys (for the cross-shard exchange) and/or decoded rows / dists / counts."""
         flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
+        vp = lambda p: C.c_void_p(int(p)) if p else None
         N.check(self._lib.rag_store_query_dev(self._h, int(B), C.c_void_p(int(queries_ptr)), int(k), int(mask_slot),
-                                              flags, int(row_base), C.c_void_p(int(out_keys_ptr)),
-                                              C.c_void_p(int(stream))))
+                                              flags, int(row_base), vp(out_keys_ptr), vp(out_rows_ptr),
+                                              vp(out_dists_ptr), vp(out_counts_ptr), vp(stream)))
 
     def last_query_info(self):
         ms, regime, launches = C.c_float(), C.c_int32(), C.c_int32()

@@ -79,6 +79,11 @@ class ShardedSearcher:
         B = q_dev.shape[0]
         b = self._buffers(B, k)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.world == 1:      # one shard: the store's own kernels emit the final result, no exchange
+            self.store.query_device(q_dev.data_ptr(), B, k, 0, stream=stream, mask_slot=mask_slot,
+                                    row_base=self.row_base, regime=regime, out_rows_ptr=b["rows"].data_ptr(),
+                                    out_dists_ptr=b["dists"].data_ptr(), out_counts_ptr=b["counts"].data_ptr())
+            return b["rows"], b["dists"], b["counts"]
         self.store.query_device(q_dev.data_ptr(), B, k, b["local"].data_ptr(), stream=stream,
                                 mask_slot=mask_slot, row_base=self.row_base, regime=regime)
         gathered = exchange_candidates(b["local"], self.world, self.group)

@@ -315,7 +315,7 @@ def test_auto_regime_switches_on_batch_size():
     try:
         st.upsert(x)
         f32.upsert(x)
-        st.query(x[:4], 5)
+        st.query(x[:2], 5)
         assert st.last_query_info()["regime"] == "stream"
         st.query(x[:64], 5)
         assert st.last_query_info()["regime"] == "tensor"
