@@ -60,7 +60,15 @@ struct QueryCtx {
   unsigned char* d_buf = nullptr;
   size_t d_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  unsigned int* d_tickets = nullptr;     // kMaxTickets zeroed counters, self-resetting (scan kernel)
+  static constexpr int kMaxTickets = 4096;
 
+  int ensure_tickets() {
+    if (d_tickets) return RAG_OK;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&d_tickets), kMaxTickets * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(d_tickets, 0, kMaxTickets * sizeof(unsigned int), stream));
+    return RAG_OK;
+  }
   int ensure_host(size_t bytes) {
     if (bytes <= h_bytes) return RAG_OK;
     if (h_pin) cudaFreeHost(h_pin);
@@ -86,6 +94,7 @@ struct QueryCtx {
     if (stream && own_stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
     if (h_pin) cudaFreeHost(h_pin);
     if (d_buf) cudaFree(d_buf);
+    if (d_tickets) cudaFree(d_tickets);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
   }
@@ -375,23 +384,31 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
     S = tres.S;
     if (timed) CUDA_TRY(cudaEventRecord(c->ev1, st));
   } else {
-    PrepArgs pa{};
-    pa.src = d_queries_raw; pa.B = B; pa.dim = s->dim; pa.row_elems = s->row_elems;
-    pa.normalise = (s->space == RAG_SPACE_COSINE);
-    pa.round_bf16 = (s->dtype == RAG_DTYPE_BF16);
-    pa.q_f32 = d_q; pa.q_bf16 = nullptr; pa.q_norm2 = nullptr;
-    pa.init_keys = nullptr; pa.init_keys_n = 0;
-    pa.init_zero = d_state; pa.init_zero_n = (int64_t)B;
-    CUDA_TRY(launch_prep_queries(pa, st));
-    launches++;
+    static const bool fused = !(getenv("RAG_B200_FUSED_MERGE") && atoi(getenv("RAG_B200_FUSED_MERGE")) == 0);
+    if (fused) {
+      int rc2 = c->ensure_tickets();
+      if (rc2 != RAG_OK) return rc2;
+      if (B > QueryCtx::kMaxTickets) return fail(RAG_EINVAL, "batch %d exceeds %d", B, QueryCtx::kMaxTickets);
+    } else {          // unfused debugging mode: separate prep and merge kernels
+      PrepArgs pa{};
+      pa.src = d_queries_raw; pa.B = B; pa.dim = s->dim; pa.row_elems = s->row_elems;
+      pa.normalise = (s->space == RAG_SPACE_COSINE);
+      pa.round_bf16 = (s->dtype == RAG_DTYPE_BF16);
+      pa.q_f32 = d_q; pa.q_bf16 = nullptr; pa.q_norm2 = nullptr;
+      pa.init_keys = nullptr; pa.init_keys_n = 0; pa.init_zero = nullptr; pa.init_zero_n = 0;
+      CUDA_TRY(launch_prep_queries(pa, st));
+      launches++;
+    }
     ScanArgs sa{};
     sa.vectors = s->d_vectors; sa.dtype = s->dtype; sa.row_elems = s->row_elems;
     sa.cpr = (int)(s->row_bytes / 16);
     sa.n_rows = s->rows; sa.live = s->d_live; sa.filter = filter; sa.filter_words = fwords;
-    sa.queries = d_q; sa.B = B; sa.k = k; sa.l2 = (s->space == RAG_SPACE_L2);
+    sa.B = B; sa.k = k; sa.l2 = (s->space == RAG_SPACE_L2);
     sa.grid_x = grid_x;
-    static const bool fused = !(getenv("RAG_B200_FUSED_MERGE") && atoi(getenv("RAG_B200_FUSED_MERGE")) == 0);
-    sa.partial = d_partial; sa.done = fused ? reinterpret_cast<unsigned int*>(d_state) : nullptr; sa.merge_keys_cap = 0;
+    sa.partial = d_partial; sa.done = fused ? c->d_tickets : nullptr; sa.merge_keys_cap = 0;
+    sa.queries = fused ? nullptr : d_q;
+    sa.queries_raw = fused ? d_queries_raw : nullptr;
+    sa.dim = s->dim; sa.normalise = (s->space == RAG_SPACE_COSINE); sa.round_bf16 = (s->dtype == RAG_DTYPE_BF16);
     sa.row_base = row_base;
     sa.out_keys = out.keys; sa.out_rows = out.rows; sa.out_dists = out.dists; sa.out_counts = out.counts;
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));

@@ -20,7 +20,9 @@ struct ScanArgs {
   const uint32_t* live;     // bitmap, ceil(n_rows/32) words valid, bit=1 live
   const uint32_t* filter;   // optional bitmap (nullptr = all pass)
   int64_t filter_words;     // words available in `filter`
-  const float* queries;     // [B][row_elems] prepared fp32
+  const float* queries;     // [B][row_elems] prepared fp32, or nullptr when queries_raw is given
+  const float* queries_raw; // [B][dim] raw fp32: the kernel normalises / rounds them itself (saves a launch)
+  int dim, normalise, round_bf16;
   int B;
   int k;
   int l2;                   // 1: d = sum((q-x)^2), 0: d = 1 - q.x
@@ -28,7 +30,7 @@ struct ScanArgs {
   // fused cross-CTA merge: every CTA publishes its sorted top-k, the LAST CTA of a query
   // group to finish (atomic ticket) merges all of them and emits the final result.
   uint64_t* partial;        // [grid_x][B][k] keys (ascending per list)
-  unsigned int* done;       // [ceil(B / QB)] tickets, zero-initialised (prep kernel)
+  unsigned int* done;       // [ceil(B / QB)] tickets, zero on entry; the last CTA re-zeroes its ticket
   int merge_keys_cap;       // keys of dynamic shared memory usable by the final in-smem sort (power of two)
   uint32_t row_base;        // added to emitted rows (multi-GPU: this shard's first global row)
   uint64_t* out_keys;       // [B][k] or nullptr

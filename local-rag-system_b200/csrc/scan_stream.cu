@@ -111,10 +111,36 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(QB) * row_elems * sizeof(float));
 
   // ---- stage queries (fp32, chunk-major so that lanes read consecutive float4) ----
+  // With queries_raw the CTA prepares them itself exactly as prep_queries_kernel would (same
+  // lane-strided summation order -> bit-identical values in both regimes): cosine stores scale
+  // by 1/|q|, bf16 stores round to bf16.
+  __shared__ float s_scale[QB];
+  if (a.queries_raw != nullptr) {
+    if (warp < QB) {
+      const int b = b0 + warp;
+      float ss = 0.0f;
+      if (a.normalise && b < a.B) {
+        const float* src = a.queries_raw + static_cast<size_t>(b) * a.dim;
+        for (int e = lane; e < a.dim; e += 32) { const float x = src[e]; ss = fmaf(x, x, ss); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      }
+      if (lane == 0) s_scale[warp] = a.normalise ? (ss > 0.0f ? rsqrtf(ss) : 0.0f) : 1.0f;
+    }
+    __syncthreads();
+  }
   for (int idx = threadIdx.x; idx < QB * row_elems; idx += blockDim.x) {
     int qb = idx / row_elems, e = idx - qb * row_elems;
     int b = b0 + qb;
-    float val = (b < a.B) ? a.queries[static_cast<size_t>(b) * row_elems + e] : 0.0f;
+    float val = 0.0f;
+    if (b < a.B) {
+      if (a.queries_raw != nullptr) {
+        val = (e < a.dim) ? a.queries_raw[static_cast<size_t>(b) * a.dim + e] * s_scale[qb] : 0.0f;
+        if (a.round_bf16) val = __bfloat162float(__float2bfloat16_rn(val));
+      } else {
+        val = a.queries[static_cast<size_t>(b) * row_elems + e];
+      }
+    }
     int dst;
     if constexpr (BF16) {
       int c = e >> 3, w = e & 7;
@@ -238,6 +264,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   __syncthreads();
   if (!s_flag) return;
   __threadfence();
+  if (threadIdx.x == 0) a.done[blockIdx.y] = 0u;    // ticket is clean again for the next launch
 
   const int S = gridDim.x;
   const int total = S * k;
