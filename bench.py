@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check one batch against a torch fp32 brute force")
+    ap.add_argument("--extra-batches", default="1024",
+                    help="comma list of further batch sizes measured device-resident and reported under 'regimes'")
     return ap.parse_args()
 
 
@@ -280,6 +282,12 @@ def main():
         kms.append(info["kernel_ms"])
         regime_seen = info["regime"]
     kernel_ms = statistics.mean(kms)
+    timing = "CUDA events around the kernel launch on the engine's stream (sync API), mean of %d" % len(kms)
+    if regime_seen == "stream" and world == 1:
+        # a step IS one launch of this kernel (query preparation and merge are fused into it):
+        # use the timed region itself
+        kernel_ms = total_ms / K
+        timing = "timed region: one launch per step, CUDA events on the launching stream, mean of %d" % K
     pk = peaks()
     row_bytes = args.dim * (2 if args.dtype == "bf16" else 4)
     if regime_seen == "tensor":
@@ -287,14 +295,36 @@ def main():
         achieved = flops / (kernel_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " burst",
-                "kernel": "gemm_topk", "kernel_ms": kernel_ms}
+                "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"],
+                "kernel": "gemm_topk_kernel", "kernel_ms": kernel_ms}
+        hbm = float(n_local) * row_bytes / (kernel_ms / 1e3) / 1e9
+        if hbm / pk["hbm_gbs"] > roof["frac"]:      # small batches in the tensor kernel are HBM-bound
+            roof = {"bound": "hbm", "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": hbm / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                    "kernel": "gemm_topk_kernel", "kernel_ms": kernel_ms}
     else:
         alg_bytes = float(n_local) * row_bytes + n_local / 8.0
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                 "kernel": "scan_stream_kernel", "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
-                "frac_of_8TBs_nominal": achieved / 8000.0}
+                "frac_of_8TBs_nominal": achieved / 8000.0, "timing": timing}
+
+    regimes = []
+    for xb in [int(v) for v in args.extra_batches.split(",") if v.strip()]:
+        if xb == B:
+            continue
+        regimes.append(measure_extra(args, store, searcher, xb, k, dev, world, n_local, pk, barrier))
+
+    # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/traffic.json),
+    # valid only for the shard size it was captured at
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        for ent in json.load(open(tpath)).get("kernels", []):
+            if (ent["kernel"] == roof["kernel"] and ent["rows"] == n_local and ent["dim"] == args.dim
+                    and ent["dtype"] == args.dtype and ent["batch"] == B):
+                roof["traffic"] = ent["dram_bytes_per_launch"]
+                roof["traffic_source"] = ent["source"]
 
     if rank == 0:
         line = {
@@ -313,6 +343,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roof,
             "clocks": clocks,
+            "regimes": regimes,
         }
         if world == 1 and not args.no_cpu_baseline:
             qps, dt, sample, cores = cpu_exact_qps(args)
@@ -322,6 +353,50 @@ def main():
     store.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_extra(args, store, searcher, B, k, dev, world, n_local, pk, barrier):
+    """Device-resident QPS + roofline of another batch size (the tensor-core regime by default)."""
+    import torch
+    import torch.distributed as dist
+    W, K = 3, 30
+    q_dev = torch.from_numpy(make_queries(W + K, B, args.dim, seed=99)).to(dev)
+    for i in range(W):
+        searcher.search_device(q_dev[i], k, regime=args.regime)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        searcher.search_device(q_dev[W + i], k, regime=args.regime)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    kms = []
+    q_host = q_dev[:5].cpu().numpy()
+    regime_seen = None
+    for i in range(5):
+        store.query(q_host[i], k, regime=args.regime)
+        info = store.last_query_info()
+        kms.append(info["kernel_ms"])
+        regime_seen = info["regime"]
+    kernel_ms = statistics.mean(kms)
+    row_bytes = args.dim * (2 if args.dtype == "bf16" else 4)
+    out = {"batch": B, "value": B / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "regime": regime_seen}
+    flops = 2.0 * B * n_local * args.dim
+    hbm = (float(n_local) * row_bytes) / (kernel_ms / 1e3) / 1e9
+    tf = flops / (kernel_ms / 1e3) / 1e12
+    if regime_seen == "tensor" and tf / pk["bf16_tflops"] > hbm / pk["hbm_gbs"]:
+        out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                           "frac": tf / pk["bf16_tflops"], "frac_of_sustained_peak": tf / pk["bf16_tflops_sustained"],
+                           "kernel": "gemm_topk_kernel", "kernel_ms": kernel_ms}
+    else:
+        out["roofline"] = {"bound": "hbm", "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                           "frac": hbm / pk["hbm_gbs"], "kernel": "gemm_topk_kernel" if regime_seen == "tensor"
+                           else "scan_stream_kernel", "kernel_ms": kernel_ms}
+    return out
 
 
 def verify(args, store, searcher, q, dev, world):
