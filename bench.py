@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check one batch against a torch fp32 brute force")
+    ap.add_argument("--selectivity", type=float, default=0.0,
+                    help="config 4: apply a `where` bitmap passing this fraction of rows (0 = no filter)")
+    ap.add_argument("--tombstones", type=float, default=0.0, help="config 4: delete this fraction of rows first")
     ap.add_argument("--extra-batches", default="1024",
                     help="comma list of further batch sizes measured device-resident and reported under 'regimes'")
     return ap.parse_args()
@@ -214,6 +217,19 @@ def main():
     build_s = time.perf_counter() - t_build0
     assert store.count() == n_local
 
+    mask_slot = -1
+    live_frac = 1.0
+    if args.tombstones > 0:
+        rng = np.random.default_rng(77 + rank)
+        dead = np.nonzero(rng.random(n_local) < args.tombstones)[0]
+        store.delete(dead)
+        live_frac *= 1.0 - len(dead) / max(n_local, 1)
+    if args.selectivity > 0:
+        rng = np.random.default_rng(99 + rank)
+        passing = rng.random(n_local) < args.selectivity     # bucket = hash(row) % 100 < s, as a bitmap
+        store.set_mask(0, passing)
+        mask_slot = 0
+        live_frac *= float(passing.mean())
     searcher = ShardedSearcher(store, rank, world, row_base=rank * stride)
     B, k, K, W = args.batch, args.k, args.steps, max(args.warmup, 3)
     q_host = torch.from_numpy(make_queries(W + K, B, args.dim)).pin_memory()
@@ -229,7 +245,7 @@ def main():
 
     # ---- device-resident timing: `value` ----
     for i in range(W):
-        searcher.search_device(q_dev[i], k, regime=args.regime)
+        searcher.search_device(q_dev[i], k, mask_slot=mask_slot, regime=args.regime)
     barrier()
     launches0 = store.kernel_launches()
     sampler = ClockSampler(local_rank)
@@ -238,7 +254,7 @@ def main():
     barrier()
     ev[0].record()
     for i in range(K):
-        searcher.search_device(q_dev[W + i], k, regime=args.regime)
+        searcher.search_device(q_dev[W + i], k, mask_slot=mask_slot, regime=args.regime)
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop()
@@ -253,7 +269,7 @@ def main():
 
     # ---- end to end through the host-buffer API: `e2e` ----
     for i in range(W):
-        searcher.search(q_host[i].numpy(), k, regime=args.regime)
+        searcher.search(q_host[i].numpy(), k, mask_slot=mask_slot, regime=args.regime)
     barrier()
     t0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True)
@@ -262,7 +278,7 @@ def main():
     lat = []
     for i in range(K):
         ts = time.perf_counter()
-        searcher.search(q_host[W + i].numpy(), k, regime=args.regime)
+        searcher.search(q_host[W + i].numpy(), k, mask_slot=mask_slot, regime=args.regime)
         lat.append((time.perf_counter() - ts) * 1e3)
     e1.record()
     barrier()
@@ -277,7 +293,7 @@ def main():
     kms = []
     regime_seen = None
     for i in range(min(K, 50)):
-        store.query(q_host[W + i].numpy(), k, regime=args.regime)
+        store.query(q_host[W + i].numpy(), k, mask_slot=mask_slot, regime=args.regime)
         info = store.last_query_info()
         kms.append(info["kernel_ms"])
         regime_seen = info["regime"]
@@ -303,7 +319,8 @@ def main():
                     "frac": hbm / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                     "kernel": "gemm_topk_kernel", "kernel_ms": kernel_ms}
     else:
-        alg_bytes = float(n_local) * row_bytes + n_local / 8.0
+        # bytes the kernel is designed to touch: rows that are live and pass the filter, plus the bitmaps
+        alg_bytes = float(n_local) * live_frac * row_bytes + n_local / 8.0 * (2 if mask_slot >= 0 else 1)
         achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
@@ -314,7 +331,7 @@ def main():
     for xb in [int(v) for v in args.extra_batches.split(",") if v.strip()]:
         if xb == B:
             continue
-        regimes.append(measure_extra(args, store, searcher, xb, k, dev, world, n_local, pk, barrier))
+        regimes.append(measure_extra(args, store, searcher, xb, k, dev, world, n_local, pk, barrier, mask_slot))
 
     # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/traffic.json),
     # valid only for the shard size it was captured at
@@ -334,7 +351,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args), "batch": B, "k": k, "space": args.space,
                        "rows_per_gpu": n_local, "sharding": f"row-wise x{world}, all-gather of Bxk keys + merge kernel",
-                       "regime": regime_seen, "l2_flush": "inputs larger than L2 (shard bytes >> 126 MB)",
+                       "regime": regime_seen, "where_selectivity": args.selectivity or None,
+                       "tombstone_fraction": args.tombstones or None, "l2_flush": "inputs larger than L2 (shard bytes >> 126 MB)",
                        "build_seconds": round(build_s, 2)},
             "p50_ms": per_step[len(per_step) // 2], "p95_ms": per_step[int(len(per_step) * 0.95)],
             "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": B * args.dim * 4,
@@ -355,19 +373,19 @@ def main():
         dist.destroy_process_group()
 
 
-def measure_extra(args, store, searcher, B, k, dev, world, n_local, pk, barrier):
+def measure_extra(args, store, searcher, B, k, dev, world, n_local, pk, barrier, mask_slot=-1):
     """Device-resident QPS + roofline of another batch size (the tensor-core regime by default)."""
     import torch
     import torch.distributed as dist
     W, K = 3, 30
     q_dev = torch.from_numpy(make_queries(W + K, B, args.dim, seed=99)).to(dev)
     for i in range(W):
-        searcher.search_device(q_dev[i], k, regime=args.regime)
+        searcher.search_device(q_dev[i], k, mask_slot=mask_slot, regime=args.regime)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        searcher.search_device(q_dev[W + i], k, regime=args.regime)
+        searcher.search_device(q_dev[W + i], k, mask_slot=mask_slot, regime=args.regime)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -378,7 +396,7 @@ def measure_extra(args, store, searcher, B, k, dev, world, n_local, pk, barrier)
     q_host = q_dev[:5].cpu().numpy()
     regime_seen = None
     for i in range(5):
-        store.query(q_host[i], k, regime=args.regime)
+        store.query(q_host[i], k, mask_slot=mask_slot, regime=args.regime)
         info = store.last_query_info()
         kms.append(info["kernel_ms"])
         regime_seen = info["regime"]

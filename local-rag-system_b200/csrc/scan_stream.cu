@@ -89,15 +89,19 @@ __device__ __forceinline__ float chunk_acc(float acc, const uint4& v, const floa
   return acc;
 }
 
-// T: float or __nv_bfloat16.  QB queries share one pass.  NJ > 0: row is exactly
-// NJ x 32 chunks (fully unrolled, no guards); NJ == 0: any row length.
-// R rows in flight per warp.
-template <bool BF16, int QB, int NJ, int R, bool L2>
+// BF16: element type.  QB queries share one pass.  LPR lanes cooperate on one row (32, or a
+// sub-warp of 16 / 8 for narrow rows, so that e.g. a 768-byte row = 3 x 16 lanes x 16 B keeps
+// every lane busy; the 32/LPR sub-warps of a warp work on different rows).  NJ > 0: a row is
+// exactly NJ x LPR chunks (fully unrolled, no guards); NJ == 0: any row length (LPR = 32).
+// R row slots in flight per warp, i.e. R x 32/LPR rows.
+template <bool BF16, int QB, int NJ, int R, bool L2, int LPR>
 __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const ScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int V = R * QB;
-  static_assert(V <= 32, "R*QB must fit one warp");
-  constexpr int SHIFT = 5 - Log2<V>::value;
+  constexpr int G = 32 / LPR;                      // rows per slot
+  static_assert(V <= LPR, "R*QB must fit the lanes of one row");
+  static_assert(NJ > 0 || LPR == 32, "generic row length needs the full warp");
+  constexpr int SHIFT = Log2<LPR>::value - Log2<V>::value;
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -154,10 +158,12 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   __syncthreads();
 
   // lane's value index after the multi-reduce, fixed for the whole kernel
-  const int my_idx = lane >> SHIFT;
+  const int sl = lane & (LPR - 1);                 // lane within its row group
+  const int grp = lane / LPR;                      // which of the slot's G rows this lane works on
+  const int my_idx = sl >> SHIFT;
   const int my_i = my_idx / QB;
   const int my_qb = my_idx - my_i * QB;
-  const bool rep = (lane & ((1 << SHIFT) - 1)) == 0;
+  const bool rep = (sl & ((1 << SHIFT) - 1)) == 0;
   uint64_t my_tau = kEmptyKey;   // current k-th best key of (this warp, my_qb)
 
   const uint4* vec = reinterpret_cast<const uint4*>(a.vectors);
@@ -169,11 +175,16 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     if (a.filter != nullptr) m &= (blk < a.filter_words) ? __ldg(a.filter + blk) : 0u;
     const uint4* bbase = vec + static_cast<size_t>(blk) * kRowsPerBlock * cpr;
     while (m) {
-      int r[R];
+      int r[R];                                      // this lane's row in each slot (-1: none)
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        r[i] = m ? (__ffs(m) - 1) : -1;
-        m &= (m - 1);
+        r[i] = -1;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int bit = m ? (__ffs(m) - 1) : -1;
+          m &= (m - 1);
+          if (G == 1 || g == grp) r[i] = bit;
+        }
       }
       float acc[V];
 #pragma unroll
@@ -185,13 +196,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         for (int i = 0; i < R; ++i) {
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            v[i][j] = (r[i] >= 0) ? ldg_stream(bbase + static_cast<size_t>(r[i]) * cpr + j * 32 + lane)
+            v[i][j] = (r[i] >= 0) ? ldg_stream(bbase + static_cast<size_t>(r[i]) * cpr + j * LPR + sl)
                                   : make_uint4(0u, 0u, 0u, 0u);
           }
         }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          const int c = j * 32 + lane;
+          const int c = j * LPR + sl;
 #pragma unroll
           for (int qb = 0; qb < QB; ++qb) {
             const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         }
       }
 
-      const float total = Fold<V, 16>::run(acc, lane);
+      const float total = Fold<V, LPR / 2>::run(acc, lane);
       int myr = r[0];
 #pragma unroll
       for (int i = 1; i < R; ++i) myr = (my_i == i) ? r[i] : myr;
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         const int src = __ffs(bal) - 1;
         bal &= (bal - 1);
         const uint64_t ck = shfl_u64(key, src);
-        const int sidx = src >> SHIFT;
+        const int sidx = (src & (LPR - 1)) >> SHIFT;
         const int cqb = sidx - (sidx / QB) * QB;
         uint64_t* L = lists + (static_cast<size_t>(cqb) * kScanWarps + warp) * kpad;
         if (ck < L[k - 1]) {   // tau may have tightened since the ballot
@@ -413,18 +424,18 @@ size_t scan_total_smem(int QB, int row_elems, int k, int grid_x, int* merge_cap)
   return need;
 }
 
-template <bool BF16, int QB, int NJ, int R>
+template <bool BF16, int QB, int NJ, int R, int LPR>
 cudaError_t launch_one(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
   if (a.l2) {
-    auto kern = scan_stream_kernel<BF16, QB, NJ, R, true>;
+    auto kern = scan_stream_kernel<BF16, QB, NJ, R, true, LPR>;
     if (smem > 48 * 1024) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
     }
     kern<<<grid, kScanThreads, smem, st>>>(a);
   } else {
-    auto kern = scan_stream_kernel<BF16, QB, NJ, R, false>;
+    auto kern = scan_stream_kernel<BF16, QB, NJ, R, false, LPR>;
     if (smem > 48 * 1024) {
       e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       if (e != cudaSuccess) return e;
@@ -436,13 +447,18 @@ cudaError_t launch_one(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t s
 
 template <bool BF16, int QB>
 cudaError_t launch_qb(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  // rows in flight per warp chosen so that R*NJ ~ 12 independent 16-byte loads per lane
+  // row slots in flight per warp chosen so that every lane has ~12 independent 16-byte loads
+  // outstanding and R*QB fits the lanes that share a row
   constexpr int R4 = (QB <= 8) ? 4 : 2;
-  if (a.cpr == 96) return launch_one<BF16, QB, 3, R4>(a, grid, smem, st);    // 768-d bf16, 384-d fp32
-  if (a.cpr == 192) return launch_one<BF16, QB, 6, 2>(a, grid, smem, st);    // 1536-d bf16, 768-d fp32
-  if (a.cpr == 64) return launch_one<BF16, QB, 2, R4>(a, grid, smem, st);    // 512-d bf16, 256-d fp32
-  if (a.cpr == 128) return launch_one<BF16, QB, 4, 2>(a, grid, smem, st);    // 1024-d bf16, 512-d fp32
-  return launch_one<BF16, QB, 0, R4>(a, grid, smem, st);
+  constexpr int R16 = (QB <= 4) ? 4 : 2;          // 16 lanes per row: R*QB <= 16
+  constexpr int R8 = (QB <= 2) ? 4 : (QB <= 4 ? 2 : 1);
+  if (a.cpr == 96) return launch_one<BF16, QB, 3, R4, 32>(a, grid, smem, st);    // 768-d bf16, 384-d fp32
+  if (a.cpr == 192) return launch_one<BF16, QB, 6, 2, 32>(a, grid, smem, st);    // 1536-d bf16, 768-d fp32
+  if (a.cpr == 64) return launch_one<BF16, QB, 2, R4, 32>(a, grid, smem, st);    // 512-d bf16, 256-d fp32
+  if (a.cpr == 128) return launch_one<BF16, QB, 4, 2, 32>(a, grid, smem, st);    // 1024-d bf16, 512-d fp32
+  if (a.cpr == 48) return launch_one<BF16, QB, 3, R16, 16>(a, grid, smem, st);   // 384-d bf16, 192-d fp32
+  if (a.cpr == 24) return launch_one<BF16, QB, 3, R8, 8>(a, grid, smem, st);     // 192-d bf16, 96-d fp32
+  return launch_one<BF16, QB, 0, R4, 32>(a, grid, smem, st);
 }
 
 }  // namespace

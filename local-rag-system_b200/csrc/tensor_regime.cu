@@ -208,7 +208,10 @@ struct Args {
   uint64_t* partial;             // [cpm][B][k]
 };
 
-// per-thread running top-k.  KL <= 16: registers (fully unrolled); larger: local memory.
+// per-thread running top-k.  KL <= 16: sorted list, fully unrolled (registers / L1-resident);
+// larger k: a binary MAX-heap in local memory (root = current k-th best): an insertion is a
+// root replacement + sift-down, O(log k) instead of the O(k) shift of a sorted list -- with
+// k = 100 the sorted list made the epilogue, not the tensor pipe, the bottleneck.
 template <int KL>
 struct TopList {
   uint64_t e[KL];
@@ -223,7 +226,7 @@ struct TopList {
       for (int i = 0; i < KL; ++i) t = (i == k - 1) ? e[i] : t;
       return t;
     } else {
-      return e[k - 1];
+      return e[0];
     }
   }
   // precondition: key < kth(k)
@@ -237,9 +240,41 @@ struct TopList {
         key = lt ? cur : key;
       }
     } else {
-      int i = k - 1;
-      while (i > 0 && e[i - 1] > key) { e[i] = e[i - 1]; --i; }
+      int i = 0;
+      for (;;) {                       // sift the new key down from the root
+        const int l = 2 * i + 1, r = l + 1;
+        if (l >= k) break;
+        const uint64_t lv = e[l];
+        const uint64_t rv = (r < k) ? e[r] : 0ull;
+        const int c = (rv > lv) ? r : l;
+        const uint64_t cv = (rv > lv) ? rv : lv;
+        if (cv <= key) break;
+        e[i] = cv;
+        i = c;
+      }
       e[i] = key;
+    }
+  }
+  // ascending order in e[0..k) (heap sort for the heap variant; the list already is)
+  __device__ __forceinline__ void finalize(int k) {
+    if constexpr (KL > 16) {
+      for (int n = k - 1; n > 0; --n) {
+        const uint64_t key = e[n];     // move the max to its final slot, re-insert the displaced key
+        e[n] = e[0];
+        int i = 0;
+        for (;;) {
+          const int l = 2 * i + 1, r = l + 1;
+          if (l >= n) break;
+          const uint64_t lv = e[l];
+          const uint64_t rv = (r < n) ? e[r] : 0ull;
+          const int c = (rv > lv) ? r : l;
+          const uint64_t cv = (rv > lv) ? rv : lv;
+          if (cv <= key) break;
+          e[i] = cv;
+          i = c;
+        }
+        e[i] = key;
+      }
     }
   }
 };
@@ -413,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     }
     // ---- emit this thread's list: partial[cj][b][0..k) ----
     if (q_valid) {
+      top.finalize(k);
       uint64_t* out = a.partial + (static_cast<size_t>(cj) * a.B + b) * k;
       if constexpr (KL <= 16) {
 #pragma unroll

@@ -64,6 +64,13 @@ CASES = [
     ("cosine", "f32", 4096, 256, 20, 10),  # > 8 queries: several corpus passes in the stream regime
     ("l2", "bf16", 2500, 1536, 3, 64),
     ("cosine", "f32", 300, 1024, 1, 300),  # k == n
+    # narrow rows: 16 or 8 lanes per row (sub-warp mode of the stream kernel)
+    ("cosine", "bf16", 5000, 384, 1, 10),
+    ("cosine", "bf16", 5000, 384, 2, 10),
+    ("cosine", "bf16", 4000, 192, 3, 10),
+    ("ip", "f32", 3000, 96, 8, 10),
+    ("cosine", "f32", 2500, 192, 1, 5),
+    ("l2", "f32", 2500, 192, 7, 12),
 ]
 
 
