@@ -50,6 +50,10 @@ def parse():
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", action="store_true", help="check one batch against a torch fp32 brute force")
+    ap.add_argument("--hnsw-baseline", action="store_true",
+                    help="also build the CPU HNSW restatement (Chroma defaults) on a small sample and report "
+                         "its recall / QPS under cpu_baseline.hnsw_restatement (slow: ~1.6 ms per inserted vector)")
+    ap.add_argument("--hnsw-sample-rows", type=int, default=20_000)
     ap.add_argument("--selectivity", type=float, default=0.0,
                     help="config 4: apply a `where` bitmap passing this fraction of rows (0 = no filter)")
     ap.add_argument("--tombstones", type=float, default=0.0, help="config 4: delete this fraction of rows first")
@@ -140,6 +144,39 @@ def cpu_exact_qps(args, threads=None, seconds_budget=25.0):
     cores = os.cpu_count() or 1
     return qps_full, dt, f"{n} of {args.rows} rows x {args.dim} fp32, batch {args.batch}, {reps} reps; " \
                          f"time scaled linearly in rows", cores
+
+
+def hnsw_baseline(args):
+    """Reference-STYLE comparator: an HNSW graph at the parameters of the
+    reference's shipped index (M 16, ef_construction 100) and Chroma's default search_ef 10,
+    restated in C (oracle/hnsw_restatement.c -- NOT Chroma itself, which cannot be installed
+    here), on a bounded sample.  Reports recall@k against exact search on the same sample, and
+    recall@1 on queries planted next to a corpus row.  On isotropic random data in hundreds of
+    dimensions graph search at ef = 10 is close to useless; real embeddings behave better."""
+    from oracle.exact_search import fast_topk_f32, prepare_corpus
+    from oracle.hnsw import HnswIndex
+    n = min(args.hnsw_sample_rows, args.rows)
+    rng = np.random.default_rng(1234)
+    x = prepare_corpus("cosine", rng.standard_normal((n, args.dim), dtype=np.float32))
+    nq = 512
+    q = prepare_corpus("cosine", rng.standard_normal((nq, args.dim), dtype=np.float32))
+    planted = rng.choice(n, nq // 2, replace=False)
+    q[: nq // 2] = prepare_corpus("cosine", x[planted] + 0.05 * rng.standard_normal((nq // 2, args.dim), dtype=np.float32))
+    t0 = time.perf_counter()
+    idx = HnswIndex(x)
+    build_s = time.perf_counter() - t0
+    idx.query(q[:8], args.k, 10)
+    t0 = time.perf_counter()
+    ids, _ = idx.query(q, args.k, 10)
+    dt = time.perf_counter() - t0
+    want, _ = fast_topk_f32("l2", q, x, args.k)
+    recall = float(np.mean([len(set(ids[i]) & set(want[i])) / args.k for i in range(nq)]))
+    recall_planted = float(np.mean(ids[: nq // 2, 0] == planted))
+    idx.close()
+    return {"kind": "restatement of hnswlib at Chroma defaults (M=16, ef_construction=100, search_ef=10, l2); not Chroma",
+            "sample": f"{n} x {args.dim} fp32 unit-norm rows, {nq} queries (half planted at sigma 0.05)",
+            "build_seconds": round(build_s, 1), "qps": nq / dt, "threads": os.cpu_count(),
+            "recall_at_k": recall, "recall_at_1_planted": recall_planted}
 
 
 def run_reference(args):
@@ -367,6 +404,8 @@ def main():
             qps, dt, sample, cores = cpu_exact_qps(args)
             line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
                                     "sample": sample}
+            if args.hnsw_baseline:
+                line["cpu_baseline"]["hnsw_restatement"] = hnsw_baseline(args)
         print(json.dumps(line))
     store.close()
     if world > 1:

@@ -405,28 +405,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       }
       mbar_wait(accf_bar(buf), par);
       tc_fence_after();
+      // both halves of the 64-column accumulator are requested back to back, then the buffer is
+      // handed back to the MMA warp before any score is looked at
+      uint32_t vv[2][32];
+      const uint32_t acc_addr = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(buf * kAccCols);
+      tmem_ld_x32(acc_addr, vv[0]);
+      tmem_ld_x32(acc_addr + 32, vv[1]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(buf));
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld_x32(tmem_acc + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(buf * kAccCols + half * 32), v);
-        tmem_wait_ld();
-        if (half == 1) {                             // both halves are in registers: release the buffer
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acce_bar(buf));
-        }
+        const uint32_t* v = vv[half];
         float d[32];
         uint32_t cand = 0;
+        if constexpr (L2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float dot = __uint_as_float(v[j]);
-          if constexpr (L2) {
+          for (int j = 0; j < 32; ++j) {
             const float xn = __shfl_sync(0xffffffffu, half ? xn1 : xn0, j);
-            d[j] = fmaf(-2.0f, dot, qn + xn);
-          } else {
-            d[j] = 1.0f - dot;
+            d[j] = fmaf(-2.0f, __uint_as_float(v[j]), qn + xn);
+            cand |= (d[j] <= tau) ? (1u << j) : 0u;
           }
-          cand |= (d[j] <= tau) ? (1u << j) : 0u;
+        } else {
+          // cosine / ip: d = 1 - dot <= tau is pre-filtered in dot space, one FSETP per score.
+          // fl(1 - dot) <= tau implies dot >= 1 - tau - 2^-24, so the test below never loses a
+          // candidate; survivors are re-checked exactly by key.
+          const float tdot = (1.0f - tau) - 1.2e-7f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            d[j] = __uint_as_float(v[j]);
+            cand |= (d[j] >= tdot) ? (1u << j) : 0u;
+          }
         }
         cand &= half ? w1 : w0;                      // live & filter bits of these 32 rows
         if (!q_valid) cand = 0;
@@ -437,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
 #pragma unroll
           for (int jj = 0; jj < 32; ++jj) dj = (jj == j) ? d[jj] : dj;
           if (L2) dj = fmaxf(dj, 0.0f);
+          else dj = 1.0f - dj;
           const uint64_t key = make_key(dj, static_cast<uint32_t>(t * kNB + half * 32 + j));
           if (key < kth_key) {
             top.insert(key, k);
