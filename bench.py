@@ -295,9 +295,10 @@ def main():
         ev[i + 1].record()
     barrier()
     clocks = sampler.stop()
+    exchange_path = searcher.last_path
     total_ms = ev[0].elapsed_time(ev[K])
     per_step = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(K))
-    launches = store.kernel_launches() - launches0 + (K if world > 1 else 0)   # + the cross-shard merge kernel per step
+    launches = store.kernel_launches() - launches0 + (K if (world > 1 and exchange_path != "fused") else 0)   # + the cross-shard merge kernel per step
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -387,7 +388,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": workload_name(args), "batch": B, "k": k, "space": args.space,
-                       "rows_per_gpu": n_local, "sharding": f"row-wise x{world}, all-gather of Bxk keys + merge kernel",
+                       "rows_per_gpu": n_local, "sharding": sharding_desc(world, exchange_path),
                        "regime": regime_seen, "where_selectivity": args.selectivity or None,
                        "tombstone_fraction": args.tombstones or None, "l2_flush": "inputs larger than L2 (shard bytes >> 126 MB)",
                        "build_seconds": round(build_s, 2)},
@@ -407,9 +408,19 @@ def main():
             if args.hnsw_baseline:
                 line["cpu_baseline"]["hnsw_restatement"] = hnsw_baseline(args)
         print(json.dumps(line))
+    searcher.close()
     store.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharding_desc(world, exchange_path):
+    if world == 1:
+        return "one shard (no exchange)"
+    if exchange_path == "fused":
+        return (f"row-wise x{world}; scan + all-gather of Bxk keys over NVLink peer memory + merge fused in ONE launch "
+                f"per GPU (no NCCL call on the data path)")
+    return f"row-wise x{world}, NCCL all-gather of Bxk keys + merge kernel"
 
 
 def measure_extra(args, store, searcher, B, k, dev, world, n_local, pk, barrier, mask_slot=-1):

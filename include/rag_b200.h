@@ -163,6 +163,35 @@ RAG_API int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* 
                        uint64_t* out_keys_dev, int64_t* out_rows_dev, float* out_dists_dev,
                        int32_t* out_counts_dev, void* stream);
 
+/* -- fused cross-shard exchange (multi-GPU, small batches) ------------------------
+ * One process per GPU.  Instead of  scan -> NCCL all-gather -> merge kernel, the scan
+ * kernel's last CTA stores the shard's B x k keys straight into every rank's exchange
+ * buffer over NVLink (peer-mapped memory), raises a flag, waits for the other ranks'
+ * flags and merges: ONE launch per query batch per GPU, no collective call on the data
+ * path.  Serves the same reference call as rag_store_query (api/app.py:544-549).
+ *   rag_exchange_create   allocates this rank's buffer (slot_keys >= B * k of any call)
+ *   rag_exchange_handle   64-byte CUDA IPC handle of it; the caller all-gathers the
+ *                         handles of all ranks (rank order) by any means
+ *   rag_exchange_connect  maps every peer's buffer
+ * All ranks must then issue the same sequence of rag_store_query_fused_dev calls
+ * (same B, k), each on one stream per exchange; results (GLOBAL rows) land on every
+ * rank.  A rank whose peers never show up gives up after 4 s and sets the status
+ * word (rag_exchange_status) instead of hanging the GPU.
+ * rag_store_fused_ok() tells whether a (B, k, flags) batch is served by this path
+ * (stream regime, k <= 128, B * k <= slot_keys); otherwise use rag_store_query_dev +
+ * all-gather + rag_merge_keys_dev.                                                 */
+#define RAG_EXCHANGE_HANDLE_BYTES 64
+typedef struct rag_exchange rag_exchange;
+RAG_API int rag_exchange_create(int device, int rank, int world, int64_t slot_keys, rag_exchange** out);
+RAG_API int rag_exchange_handle(rag_exchange* x, void* out_handle);
+RAG_API int rag_exchange_connect(rag_exchange* x, const void* handles);
+RAG_API int rag_exchange_status(rag_exchange* x, int* timed_out);
+RAG_API int rag_exchange_destroy(rag_exchange* x);
+RAG_API int rag_store_fused_ok(const rag_store* s, const rag_exchange* x, int B, int k, int flags);
+RAG_API int rag_store_query_fused_dev(rag_store* s, rag_exchange* x, int B, const float* queries_dev, int k,
+                              int mask_slot, int flags, uint32_t row_base, int64_t* out_rows_dev,
+                              float* out_dists_dev, int32_t* out_counts_dev, void* stream);
+
 /* helpers to (de)compose keys on the host */
 RAG_API uint64_t rag_key_pack(float dist, uint32_t row);
 RAG_API float rag_key_dist(uint64_t key);

@@ -22,6 +22,7 @@ EINVAL, ECUDA, ENOMEM, ENODEV = -1, -2, -3, -4
 EMPTY_KEY = 0xFFFFFFFFFFFFFFFF
 MAX_K = 1024
 MAX_MASK_SLOTS = 16
+EXCHANGE_HANDLE_BYTES = 64
 
 _p = C.c_void_p
 _i64p = C.POINTER(C.c_int64)
@@ -55,6 +56,13 @@ SIGNATURES = {
     "rag_store_query": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
     "rag_store_query_dev": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p, _p, _p]),
     "rag_merge_keys_dev": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p, _p]),
+    "rag_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_p)]),
+    "rag_exchange_handle": (C.c_int, [_p, _p]),
+    "rag_exchange_connect": (C.c_int, [_p, _p]),
+    "rag_exchange_status": (C.c_int, [_p, _i32p]),
+    "rag_exchange_destroy": (C.c_int, [_p]),
+    "rag_store_fused_ok": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int]),
+    "rag_store_query_fused_dev": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p, _p]),
     "rag_key_pack": (C.c_uint64, [C.c_float, C.c_uint32]),
     "rag_key_dist": (C.c_float, [C.c_uint64]),
     "rag_key_row": (C.c_uint32, [C.c_uint64]),

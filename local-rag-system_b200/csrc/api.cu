@@ -113,7 +113,12 @@ struct rag_store {
   int64_t live = 0;
   void* d_vectors = nullptr;
   float* d_norms2 = nullptr;
+  float* d_max_norm2 = nullptr;          // [1] largest |stored row|^2 ever written (error bound of the split regime)
   uint32_t* d_live = nullptr;
+  // fp32 stores, tensor regime: bf16 [capacity][hi(row_elems) | lo(row_elems)] split of the rows, built on
+  // the first large-batch query, kept in step by upsert, dropped (and rebuilt lazily) when the store grows
+  __nv_bfloat16* d_shadow = nullptr;
+  std::mutex shadow_mu;
   uint32_t* d_masks[RAG_MAX_MASK_SLOTS] = {};
   int64_t mask_words[RAG_MAX_MASK_SLOTS] = {};
   std::vector<uint32_t> h_live;
@@ -134,6 +139,18 @@ struct rag_store {
   std::atomic<int> last_regime{0};
   std::atomic<int> last_launches{0};
   float last_kernel_ms = 0.0f;
+};
+
+// peer-mapped buffers for the fused scan + all-gather + merge launch (multi-GPU, one process per GPU)
+struct rag_exchange {
+  int device = 0, rank = 0, world = 1;
+  int64_t slot_keys = 0;
+  size_t bytes = 0;
+  unsigned char* d_local = nullptr;
+  std::vector<unsigned char*> peers;     // [world] base of every rank's buffer as mapped into this process
+  unsigned char** d_peers = nullptr;     // the same table on the device
+  uint32_t epoch = 0;
+  bool connected = false;
 };
 
 namespace {
@@ -233,6 +250,7 @@ int grow(rag_store* s, int64_t need) {
   if (s->d_norms2) cudaFree(s->d_norms2);
   if (s->d_live) cudaFree(s->d_live);
   s->d_vectors = nv; s->d_norms2 = nn; s->d_live = nl;
+  if (s->d_shadow) { cudaFree(s->d_shadow); s->d_shadow = nullptr; }
   s->capacity = cap;
   s->h_live.resize((size_t)cap / 32, 0u);
   if (s->tensor_plan) tensor::invalidate(s->tensor_plan);
@@ -290,7 +308,9 @@ int upsert_device_chunk(rag_store* s, const float* d_src, int64_t n, const int64
   a.normalise = (s->space == RAG_SPACE_COSINE);
   a.vectors = s->d_vectors;
   a.norms2 = s->d_norms2;
+  a.max_norm2 = s->d_max_norm2;
   a.live = s->d_live;
+  a.shadow = s->d_shadow;
   if (contig) {
     a.rows = nullptr;
     a.row0 = dst_rows_host[0];
@@ -328,7 +348,25 @@ int choose_regime(const rag_store* s, int B, int k, int flags) {
   if (!tensor_ok) return 1;
   // the stream kernel reads the corpus once per group of <= 8 queries; the tensor kernel
   // once per 128 (HBM-bound up to ~256 queries, tensor-bound beyond)
+  if (s->dtype == RAG_DTYPE_F32) return (B > tensor::kStreamMaxBatchF32) ? 2 : 1;
   return (B > tensor::kStreamMaxBatch) ? 2 : 1;
+}
+
+// fp32 store about to be searched by the tensor regime: make sure its bf16 hi/lo shadow exists
+// (read lock held: no writer is active; concurrent readers serialise on shadow_mu)
+int ensure_shadow(rag_store* s, cudaStream_t st) {
+  std::lock_guard<std::mutex> g(s->shadow_mu);
+  if (s->d_shadow) return RAG_OK;
+  __nv_bfloat16* sh = nullptr;
+  const size_t bytes = (size_t)s->capacity * 2 * s->row_elems * sizeof(__nv_bfloat16);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&sh), bytes);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RAG_ENOMEM, "cudaMalloc of %zu bytes for the split-precision shadow failed: %s", bytes, cudaGetErrorString(e)); }
+  e = launch_split_rows(reinterpret_cast<const float*>(s->d_vectors), s->row_elems, 0, s->rows, sh, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(sh); return fail(RAG_ECUDA, "building the split-precision shadow failed: %s", cudaGetErrorString(e)); }
+  s->d_shadow = sh;
+  s->launches++;
+  return RAG_OK;
 }
 
 // shard-local search on device buffers: prep -> scan -> merge.  Emits keys and/or rows.
@@ -344,20 +382,21 @@ struct SearchOut {
 size_t search_scratch_bytes(const rag_store* s, int B, int k, int grid_x) {
   size_t q = align_up((size_t)B * s->row_elems * sizeof(float), 256);
   size_t part = align_up((size_t)grid_x * B * k * sizeof(uint64_t), 256);
-  size_t st = align_up((size_t)B * sizeof(int), 256);
+  size_t st = align_up((size_t)(B + 1) * sizeof(int), 256);      // redo count + list (split-precision tensor regime)
   return q + part + st + tensor::scratch_bytes(s->dtype, s->row_elems, B, k, s->sm_count);
 }
 
 int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
-                  int mask_slot, int regime, uint32_t row_base, const SearchOut& out, bool timed) {
+                  int mask_slot, int regime, uint32_t row_base, const SearchOut& out, bool timed,
+                  rag_exchange* xchg = nullptr) {
   cudaStream_t st = c->stream;
   const int grid_x = scan_stream_grid_x(s->sm_count, s->rows);
   float* d_q = reinterpret_cast<float*>(scratch);
   size_t off = align_up((size_t)B * s->row_elems * sizeof(float), 256);
   uint64_t* d_partial = reinterpret_cast<uint64_t*>(scratch + off);
   off += align_up((size_t)grid_x * B * k * sizeof(uint64_t), 256);
-  int* d_state = reinterpret_cast<int*>(scratch + off);      // tickets [B]
-  off += align_up((size_t)B * sizeof(int), 256);
+  int* d_redo = reinterpret_cast<int*>(scratch + off);       // [0] count, [1..B] query indices
+  off += align_up((size_t)(B + 1) * sizeof(int), 256);
   unsigned char* d_tensor = scratch + off;
 
   const uint32_t* filter = nullptr;
@@ -372,7 +411,11 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   if (regime == 2) {
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     tensor::Problem p{};
-    p.vectors = s->d_vectors; p.norms2 = s->d_norms2; p.n_rows = s->rows; p.row_elems = s->row_elems;
+    if (s->dtype == RAG_DTYPE_F32) {
+      int rcs = ensure_shadow(s, st);
+      if (rcs != RAG_OK) return rcs;
+    }
+    p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.norms2 = s->d_norms2; p.n_rows = s->rows; p.row_elems = s->row_elems;
     p.dim = s->dim; p.dtype = s->dtype; p.space = s->space;
     p.live = s->d_live; p.filter = filter; p.filter_words = fwords;
     p.dense = (filter == nullptr && s->live == s->rows) ? 1 : 0;
@@ -411,6 +454,11 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
     sa.dim = s->dim; sa.normalise = (s->space == RAG_SPACE_COSINE); sa.round_bf16 = (s->dtype == RAG_DTYPE_BF16);
     sa.row_base = row_base;
     sa.out_keys = out.keys; sa.out_rows = out.rows; sa.out_dists = out.dists; sa.out_counts = out.counts;
+    if (xchg != nullptr) {
+      if (!fused) return fail(RAG_EINVAL, "the fused exchange needs the fused merge (RAG_B200_FUSED_MERGE=0 is set)");
+      sa.xchg_peers = xchg->d_peers; sa.xchg_rank = xchg->rank; sa.xchg_world = xchg->world;
+      sa.xchg_epoch = ++xchg->epoch; sa.xchg_slot_keys = xchg->slot_keys;
+    }
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     CUDA_TRY(launch_scan_stream(sa, s->sm_count, st, &launches));
     if (timed) CUDA_TRY(cudaEventRecord(c->ev1, st));
@@ -422,10 +470,12 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
     }
     S = grid_x;
   }
+  const bool split = (regime == 2 && s->dtype == RAG_DTYPE_F32);
+  const int k_kept = (regime == 2) ? tres.k_kept : k;
   MergeArgs ma{};
-  ma.keys = d_partial; ma.S = S; ma.B = B; ma.k = k; ma.row_base = row_base;
+  ma.keys = d_partial; ma.S = S; ma.B = B; ma.k = k_kept; ma.row_base = row_base;
   ma.out_keys = out.keys; ma.out_rows = out.rows; ma.out_dists = out.dists; ma.out_counts = out.counts;
-  const bool refine = (regime == 2 && s->space == RAG_SPACE_L2);
+  const bool refine = (regime == 2 && (s->space == RAG_SPACE_L2 || split));
   if (refine) {   // merge to scratch keys first, then re-score the winners exactly
     ma.row_base = 0; ma.out_keys = tres.merged; ma.out_rows = nullptr; ma.out_dists = nullptr; ma.out_counts = nullptr;
   }
@@ -434,14 +484,55 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   if (refine) {
     RefineArgs ra{};
     ra.keys = tres.merged; ra.vectors = s->d_vectors; ra.queries = tres.q_f32;
-    ra.dtype = s->dtype; ra.row_elems = s->row_elems; ra.B = B; ra.k = k; ra.row_base = row_base;
+    ra.dtype = s->dtype; ra.row_elems = s->row_elems; ra.B = B; ra.k = k; ra.k_in = k_kept;
+    ra.l2 = (s->space == RAG_SPACE_L2) ? 1 : 0; ra.row_base = row_base;
     ra.out_keys = out.keys; ra.out_rows = out.rows; ra.out_dists = out.dists; ra.out_counts = out.counts;
-    CUDA_TRY(launch_refine_l2(ra, st));
+    if (split) {
+      CUDA_TRY(cudaMemsetAsync(d_redo, 0, sizeof(int), st));
+      ra.guard_rel = 1.2e-4f; ra.q_norm2 = tres.q_norm2; ra.x_max_norm2 = s->d_max_norm2;
+      ra.redo_count = d_redo; ra.redo_list = d_redo + 1;
+    }
+    CUDA_TRY(launch_refine(ra, st));
     launches++;
+    if (split) {
+      // queries whose top-k the approximate ranking could not certify are re-run on the exact fp32
+      // stream kernel; the launch covers the worst case and exits at once when the list is empty
+      int rc2 = c->ensure_tickets();
+      if (rc2 != RAG_OK) return rc2;
+      if (B > QueryCtx::kMaxTickets) return fail(RAG_EINVAL, "batch %d exceeds %d", B, QueryCtx::kMaxTickets);
+      ScanArgs sa{};
+      sa.vectors = s->d_vectors; sa.dtype = s->dtype; sa.row_elems = s->row_elems;
+      sa.cpr = (int)(s->row_bytes / 16);
+      sa.n_rows = s->rows; sa.live = s->d_live; sa.filter = filter; sa.filter_words = fwords;
+      sa.B = B; sa.k = k; sa.l2 = (s->space == RAG_SPACE_L2);
+      sa.grid_x = grid_x;
+      sa.partial = reinterpret_cast<uint64_t*>(scratch + align_up((size_t)B * s->row_elems * sizeof(float), 256));
+      sa.done = c->d_tickets; sa.merge_keys_cap = 0;
+      sa.queries = nullptr; sa.queries_raw = d_queries_raw;
+      sa.dim = s->dim; sa.normalise = (s->space == RAG_SPACE_COSINE); sa.round_bf16 = 0;
+      sa.row_base = row_base;
+      sa.out_keys = out.keys; sa.out_rows = out.rows; sa.out_dists = out.dists; sa.out_counts = out.counts;
+      sa.q_count = d_redo; sa.q_index = d_redo + 1;
+      CUDA_TRY(launch_scan_stream(sa, s->sm_count, st, &launches));
+    }
   }
   s->launches += launches;
   s->last_launches = launches;
   s->last_regime = regime;
+  return RAG_OK;
+}
+
+// scratch of the asynchronous API: one context per caller stream
+int dev_ctx_for(rag_store* s, void* stream, QueryCtx** out) {
+  std::lock_guard<std::mutex> lg(s->dev_mu);
+  auto it = s->dev_ctx.find(stream);
+  if (it != s->dev_ctx.end()) { *out = it->second; return RAG_OK; }
+  QueryCtx* c = new (std::nothrow) QueryCtx();
+  if (!c) return fail(RAG_ENOMEM, "out of host memory");
+  c->stream = reinterpret_cast<cudaStream_t>(stream);
+  c->own_stream = false;
+  s->dev_ctx[stream] = c;
+  *out = c;
   return RAG_OK;
 }
 
@@ -501,6 +592,9 @@ int rag_store_create(int dim, int dtype, int space, int device, int64_t capacity
   e = cudaStreamCreateWithFlags(&s->admin.stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return fail(RAG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   s->admin.own_stream = true;
+  e = cudaMalloc(reinterpret_cast<void**>(&s->d_max_norm2), sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(s->d_max_norm2, 0, sizeof(float));
+  if (e != cudaSuccess) { (void)cudaGetLastError(); rag_store_destroy(s); return fail(RAG_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
   s->tensor_plan = tensor::create_plan();
   int rc = grow(s, std::max<int64_t>(capacity_hint, 1024));
   if (rc != RAG_OK) { rag_store_destroy(s); return rc; }
@@ -519,6 +613,8 @@ int rag_store_destroy(rag_store* s) {
   for (int i = 0; i < RAG_MAX_MASK_SLOTS; ++i) if (s->d_masks[i]) cudaFree(s->d_masks[i]);
   if (s->d_vectors) cudaFree(s->d_vectors);
   if (s->d_norms2) cudaFree(s->d_norms2);
+  if (s->d_max_norm2) cudaFree(s->d_max_norm2);
+  if (s->d_shadow) cudaFree(s->d_shadow);
   if (s->d_live) cudaFree(s->d_live);
   pthread_rwlock_destroy(&s->lock);
   delete s;
@@ -768,19 +864,8 @@ int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, in
   }
   if (B > batch_limit(s, k)) return fail(RAG_EINVAL, "batch %d too large for one asynchronous call (limit %d)", B, batch_limit(s, k));
   QueryCtx* c = nullptr;
-  {
-    std::lock_guard<std::mutex> lg(s->dev_mu);
-    auto it = s->dev_ctx.find(stream);
-    if (it == s->dev_ctx.end()) {
-      c = new (std::nothrow) QueryCtx();
-      if (!c) return fail(RAG_ENOMEM, "out of host memory");
-      c->stream = st;
-      c->own_stream = false;
-      s->dev_ctx[stream] = c;
-    } else {
-      c = it->second;
-    }
-  }
+  rc = dev_ctx_for(s, stream, &c);
+  if (rc != RAG_OK) return rc;
   const int regime = choose_regime(s, B, k, flags);
   if (regime < 0) return fail(RAG_EINVAL, "tensor regime does not support this store/query");
   const int grid_x = scan_stream_grid_x(s->sm_count, s->rows);
@@ -792,6 +877,114 @@ int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, in
   so.dists = out_dists_dev;
   so.counts = out_counts_dev;
   return search_device(s, c, c->d_buf, B, queries_dev, k, mask_slot, regime, row_base, so, false);
+}
+
+// ---- fused cross-shard exchange (multi-GPU, stream regime) ---------------------------------
+int rag_exchange_create(int device, int rank, int world, int64_t slot_keys, rag_exchange** out) {
+  if (!out) return fail(RAG_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (world < 1 || world > kXchgMaxWorld || rank < 0 || rank >= world)
+    return fail(RAG_EINVAL, "exchange needs 0 <= rank < world <= %d, got rank %d world %d", kXchgMaxWorld, rank, world);
+  if (slot_keys < 1 || slot_keys > (1 << 22)) return fail(RAG_EINVAL, "slot_keys must be in [1, 2^22]");
+  CUDA_TRY(cudaSetDevice(device));
+  rag_exchange* x = new (std::nothrow) rag_exchange();
+  if (!x) return fail(RAG_ENOMEM, "out of host memory");
+  x->device = device; x->rank = rank; x->world = world; x->slot_keys = slot_keys;
+  x->bytes = xchg_buffer_bytes(world, slot_keys);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&x->d_local), x->bytes);
+  if (e == cudaSuccess) e = cudaMemset(x->d_local, 0, x->bytes);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&x->d_peers), kXchgMaxWorld * sizeof(unsigned char*));
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (x->d_local) cudaFree(x->d_local);
+    delete x;
+    return fail(RAG_ENOMEM, "exchange buffer allocation failed: %s", cudaGetErrorString(e));
+  }
+  x->peers.assign((size_t)world, nullptr);
+  *out = x;
+  return RAG_OK;
+}
+
+int rag_exchange_handle(rag_exchange* x, void* out_handle) {
+  if (!x || !out_handle) return fail(RAG_EINVAL, "exchange/out is NULL");
+  static_assert(sizeof(cudaIpcMemHandle_t) == RAG_EXCHANGE_HANDLE_BYTES, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(x->device));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, x->d_local));
+  memcpy(out_handle, &h, sizeof(h));
+  return RAG_OK;
+}
+
+int rag_exchange_connect(rag_exchange* x, const void* handles) {
+  if (!x || !handles) return fail(RAG_EINVAL, "exchange/handles is NULL");
+  if (x->connected) return fail(RAG_EINVAL, "exchange is already connected");
+  CUDA_TRY(cudaSetDevice(x->device));
+  for (int g = 0; g < x->world; ++g) {
+    if (g == x->rank) { x->peers[(size_t)g] = x->d_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const unsigned char*>(handles) + (size_t)g * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peers[(size_t)g] = static_cast<unsigned char*>(p);
+  }
+  CUDA_TRY(cudaMemcpy(x->d_peers, x->peers.data(), (size_t)x->world * sizeof(unsigned char*), cudaMemcpyHostToDevice));
+  x->connected = true;
+  return RAG_OK;
+}
+
+int rag_exchange_status(rag_exchange* x, int* timed_out) {
+  if (!x || !timed_out) return fail(RAG_EINVAL, "exchange/out is NULL");
+  CUDA_TRY(cudaSetDevice(x->device));
+  uint32_t st = 0;
+  CUDA_TRY(cudaMemcpy(&st, x->d_local + kXchgStatusOff, sizeof(st), cudaMemcpyDeviceToHost));
+  *timed_out = st != 0 ? 1 : 0;
+  return RAG_OK;
+}
+
+int rag_exchange_destroy(rag_exchange* x) {
+  if (!x) return RAG_OK;
+  cudaSetDevice(x->device);
+  cudaDeviceSynchronize();
+  for (int g = 0; g < x->world; ++g)
+    if (g != x->rank && x->peers[(size_t)g]) cudaIpcCloseMemHandle(x->peers[(size_t)g]);
+  if (x->d_peers) cudaFree(x->d_peers);
+  if (x->d_local) cudaFree(x->d_local);
+  delete x;
+  return RAG_OK;
+}
+
+int rag_store_fused_ok(const rag_store* s, const rag_exchange* x, int B, int k, int flags) {
+  if (!s || !x || !x->connected || B < 1 || k < 1 || k > 128) return 0;
+  if (choose_regime(s, B, k, flags) != 1) return 0;
+  if ((int64_t)B * k > x->slot_keys) return 0;
+  if (scan_stream_groups(B, s->dtype, s->row_elems, k) > kXchgMaxGroups) return 0;
+  if (B > QueryCtx::kMaxTickets || B > batch_limit(s, k)) return 0;
+  return 1;
+}
+
+int rag_store_query_fused_dev(rag_store* s, rag_exchange* x, int B, const float* queries_dev, int k, int mask_slot,
+                              int flags, uint32_t row_base, int64_t* out_rows_dev, float* out_dists_dev,
+                              int32_t* out_counts_dev, void* stream) {
+  if (!s) return fail(RAG_EINVAL, "store is NULL");
+  if (!x || !x->connected) return fail(RAG_EINVAL, "exchange is NULL or not connected");
+  RdLock g(&s->lock);
+  int rc = check_query_args(s, B, queries_dev, k, mask_slot);
+  if (rc != RAG_OK) return rc;
+  if (!out_rows_dev) return fail(RAG_EINVAL, "out_rows_dev is NULL");
+  if (x->device != s->device) return fail(RAG_EINVAL, "exchange and store live on different devices");
+  if (!rag_store_fused_ok(s, x, B, k, flags))
+    return fail(RAG_EINVAL, "batch %d / k %d is not served by the fused exchange (use rag_store_query_dev + all-gather)", B, k);
+  CUDA_TRY(cudaSetDevice(s->device));
+  QueryCtx* c = nullptr;
+  rc = dev_ctx_for(s, stream, &c);
+  if (rc != RAG_OK) return rc;
+  const int grid_x = scan_stream_grid_x(s->sm_count, s->rows);
+  rc = c->ensure_dev(search_scratch_bytes(s, B, k, grid_x));
+  if (rc != RAG_OK) return rc;
+  SearchOut so{};
+  so.rows = out_rows_dev; so.dists = out_dists_dev; so.counts = out_counts_dev;
+  // an empty shard still takes part: it publishes empty lists and waits like everyone else
+  return search_device(s, c, c->d_buf, B, queries_dev, k, mask_slot, 1, row_base, so, false, x);
 }
 
 int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* keys_dev, uint64_t* out_keys_dev,

@@ -37,7 +37,33 @@ struct ScanArgs {
   int64_t* out_rows;        // [B][k] or nullptr
   float* out_dists;         // [B][k] or nullptr
   int32_t* out_counts;      // [B]    or nullptr
+  // Fused cross-shard exchange over NVLink peer memory (multi-GPU, optional; nullptr = off).
+  // The last CTA of a query group stores the shard's k best keys into EVERY rank's exchange
+  // buffer (peer-mapped stores), raises its flag there, waits for all ranks' flags in its own
+  // buffer, merges the `xchg_world` lists and emits the GLOBAL result: scan + all-gather +
+  // merge are one launch, no NCCL call on the data path.
+  unsigned char* const* xchg_peers;   // device array [xchg_world]: base of every rank's exchange buffer
+  int xchg_rank, xchg_world;
+  uint32_t xchg_epoch;      // >= 1, identical on every rank, +1 per call (parity picks the buffer half)
+  int64_t xchg_slot_keys;   // keys per (parity, rank) slot; B * k must fit
+  // optional device-side query list: only the first *q_count queries are searched and query i is
+  // queries_raw[q_index[i]] / results go to slot q_index[i] (nullptr = all B queries, identity)
+  const int* q_count;
+  const int* q_index;
 };
+// ---- layout of one rank's exchange buffer (identical on every rank) ----------------------
+//   u32 flags[2][kXchgMaxGroups][kXchgMaxWorld]   flags[p][y][g] = last epoch of parity p for which rank g
+//                                                 has delivered the lists of query group y
+//   u32 status[64]                                status[0] != 0: a wait timed out (peer missing)
+//   u64 keys[2][world][slot_keys]                 keys[p][g][b * k + j]
+constexpr int kXchgMaxGroups = 64;
+constexpr int kXchgMaxWorld = 32;
+constexpr size_t kXchgFlagBytes = 2ull * kXchgMaxGroups * kXchgMaxWorld * sizeof(uint32_t);
+constexpr size_t kXchgStatusOff = kXchgFlagBytes;
+constexpr size_t kXchgKeysOff = kXchgFlagBytes + 64 * sizeof(uint32_t);
+inline size_t xchg_buffer_bytes(int world, int64_t slot_keys) {
+  return kXchgKeysOff + 2ull * world * static_cast<size_t>(slot_keys) * sizeof(uint64_t);
+}
 // picks QB (queries per pass) and the kernel instantiation; returns cudaError_t
 cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st, int* launches);
 // grid_x the launcher will use for this problem (so the caller can size `partial`)
@@ -59,19 +85,31 @@ struct MergeArgs {
 };
 cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
 
-// exact l2 re-scoring + re-sort of the B x k winners (tensor regime)
+// exact re-scoring + re-sort of the B x k_in approximate winners (tensor regime); emits the best k
 struct RefineArgs {
-  const uint64_t* keys;     // [B][k] merged winners (rows local to the store)
+  const uint64_t* keys;     // [B][k_in] merged winners (rows local to the store)
   const void* vectors;
   const float* queries;     // [B][row_elems] prepared fp32
   int dtype, row_elems, B, k;
+  int k_in;                 // candidates per query (>= k)
+  int l2;                   // 1: sum((q-x)^2), 0: 1 - q.x
+  // exactness guard of the split-precision regime (nullptr = off): the candidates were ranked by
+  // approximate distances with |approx - exact| <= guard_eps.  If the list is full and its worst
+  // approximate distance is not at least 2*guard_eps beyond the exact k-th distance, a row outside
+  // the list could belong to the top k: the query index is appended to redo_list (count in
+  // redo_count) and re-run on the exact fp32 stream kernel.
+  float guard_rel;          // |approx - exact| <= guard_rel * |q| * max|x| (x 2 for l2)
+  const float* q_norm2;     // [B]
+  const float* x_max_norm2; // [1]
+  int* redo_count;
+  int* redo_list;
   uint32_t row_base;
   uint64_t* out_keys;
   int64_t* out_rows;
   float* out_dists;
   int32_t* out_counts;
 };
-cudaError_t launch_refine_l2(const RefineArgs& a, cudaStream_t st);
+cudaError_t launch_refine(const RefineArgs& a, cudaStream_t st);
 
 // ---- K1: normalise / convert on upsert ------------------------------------------
 struct UpsertArgs {
@@ -83,8 +121,15 @@ struct UpsertArgs {
   int normalise;            // cosine
   void* vectors;
   float* norms2;            // [capacity] sum of squares of the stored row
+  float* max_norm2;         // [1] running maximum of norms2 over everything ever stored (error bounds)
   uint32_t* live;
+  // optional split-precision shadow of an fp32 store for the tensor regime: row r is
+  // [hi(row_elems) | lo(row_elems)] bf16 with x = hi + lo + O(2^-17 |x|); nullptr when absent
+  __nv_bfloat16* shadow;
 };
+// (re)build the shadow of rows [row0, row0 + n) from the stored fp32 rows
+cudaError_t launch_split_rows(const float* vectors, int row_elems, int64_t row0, int64_t n,
+                              __nv_bfloat16* shadow, cudaStream_t st);
 cudaError_t launch_upsert(const UpsertArgs& a, cudaStream_t st);
 
 // K7: clear live bits
@@ -95,8 +140,9 @@ struct PrepArgs {
   const float* src;         // [B][dim]
   int B, dim, row_elems;
   int normalise, round_bf16;
+  int split;                // 1: q_bf16 rows are [hi(row_elems) | lo(row_elems)] (fp32 stores, tensor regime)
   float* q_f32;             // [B][row_elems]
-  __nv_bfloat16* q_bf16;    // [Bpad][row_elems] or nullptr (rows >= B zero-filled by caller)
+  __nv_bfloat16* q_bf16;    // [Bpad][row_elems * (split ? 2 : 1)] or nullptr (rows >= B zero-filled by caller)
   float* q_norm2;           // [B] or nullptr
   // optional initialisation of the scan kernel's merge state (done here to save launches)
   uint64_t* init_keys;      // filled with kEmptyKey (init_keys_n entries) or nullptr

@@ -112,40 +112,60 @@ __global__ void __launch_bounds__(kMergeThreads) merge_small_kernel(const MergeA
   if (lane == 0 && a.out_counts) a.out_counts[b] = cnt;
 }
 
-// ---- exact re-scoring of the k winners (tensor regime, l2 space) --------------------
-// The tensor kernel ranks by |q|^2 + |x|^2 - 2 q.x, whose cancellation error grows
-// with the norms.  The k survivors per query are re-scored here with the direct
-// sum((q-x)^2) the stream kernel uses, re-sorted and emitted, so reported distances
-// meet the same tolerance in both regimes.  One CTA per query, one warp per row.
-__global__ void __launch_bounds__(kMergeThreads) refine_l2_kernel(const RefineArgs a) {
+// ---- exact re-scoring of the approximate winners (tensor regime) --------------------------------
+// The tensor kernel ranks l2 by |q|^2 + |x|^2 - 2 q.x (cancellation error grows with the norms) and,
+// for fp32 stores, contracts bf16 hi/lo splits (~1e-6 absolute error on a unit-norm dot product).
+// The k_in >= k survivors per query are re-scored here from the stored rows with the same direct
+// fp32 arithmetic the stream kernel uses, re-sorted, and the best k emitted -- so distances meet
+// the same tolerance in both regimes and near-ties at the k-th place are decided exactly.
+// One CTA per query, one warp per row.
+__global__ void __launch_bounds__(kMergeThreads) refine_kernel(const RefineArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.x;
   const int k = a.k;
-  const int kpad = next_pow2(k);
+  const int kin = a.k_in;
+  const int kpad = next_pow2(kin);
   for (int i = threadIdx.x; i < kpad; i += blockDim.x) keys[i] = kEmptyKey;
   __syncthreads();
   const float* q = a.queries + static_cast<size_t>(b) * a.row_elems;
-  for (int j = warp; j < k; j += kMergeWarps) {
-    const uint64_t key = a.keys[static_cast<size_t>(b) * k + j];
+  for (int j = warp; j < kin; j += kMergeWarps) {
+    const uint64_t key = a.keys[static_cast<size_t>(b) * kin + j];
     if (key == kEmptyKey) continue;
     const uint32_t row = key_row(key);
     float acc = 0.0f;
     if (a.dtype == 1) {
       const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.vectors) + static_cast<size_t>(row) * a.row_elems;
-      for (int e = lane; e < a.row_elems; e += 32) { float d = __bfloat162float(x[e]) - q[e]; acc = fmaf(d, d, acc); }
+      for (int e = lane; e < a.row_elems; e += 32) {
+        const float xv = __bfloat162float(x[e]);
+        if (a.l2) { const float d = xv - q[e]; acc = fmaf(d, d, acc); } else { acc = fmaf(xv, q[e], acc); }
+      }
     } else {
       const float* x = reinterpret_cast<const float*>(a.vectors) + static_cast<size_t>(row) * a.row_elems;
-      for (int e = lane; e < a.row_elems; e += 32) { float d = x[e] - q[e]; acc = fmaf(d, d, acc); }
+      for (int e = lane; e < a.row_elems; e += 32) {
+        if (a.l2) { const float d = x[e] - q[e]; acc = fmaf(d, d, acc); } else { acc = fmaf(x[e], q[e], acc); }
+      }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) keys[j] = make_key(acc, row);
+    if (lane == 0) keys[j] = make_key(a.l2 ? acc : 1.0f - acc, row);
   }
   __syncthreads();
   block_bitonic_sort(keys, kpad);
+  if (a.redo_count != nullptr && threadIdx.x == 0) {
+    // exactness guard: candidates were the k_in best by APPROXIMATE distance.  A row outside the
+    // list has approx >= a_max, hence exact >= a_max - eps; it cannot displace the exact k-th
+    // best d_k (which may itself be over-estimated by eps) when a_max - d_k > 2 eps.
+    const uint64_t worst_in = a.keys[static_cast<size_t>(b) * kin + kin - 1];
+    if (worst_in != kEmptyKey && keys[k - 1] != kEmptyKey) {
+      const float a_max = key_dist(worst_in);
+      const float d_k = key_dist(keys[k - 1]);
+      const float eps = a.guard_rel * sqrtf(a.q_norm2[b] * a.x_max_norm2[0]) * (a.l2 ? 2.0f : 1.0f);
+      if (!(a_max - d_k > 2.0f * eps)) a.redo_list[atomicAdd(a.redo_count, 1)] = b;
+    }
+  }
   int cnt = 0;
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     uint64_t key = keys[j];
@@ -171,10 +191,10 @@ __global__ void __launch_bounds__(kMergeThreads) refine_l2_kernel(const RefineAr
 
 }  // namespace
 
-cudaError_t launch_refine_l2(const RefineArgs& a, cudaStream_t st) {
-  if (a.B <= 0 || a.k <= 0) return cudaErrorInvalidValue;
-  const size_t smem = static_cast<size_t>(next_pow2(a.k)) * sizeof(uint64_t);
-  refine_l2_kernel<<<a.B, kMergeThreads, smem, st>>>(a);
+cudaError_t launch_refine(const RefineArgs& a, cudaStream_t st) {
+  if (a.B <= 0 || a.k <= 0 || a.k_in < a.k) return cudaErrorInvalidValue;
+  const size_t smem = static_cast<size_t>(next_pow2(a.k_in)) * sizeof(uint64_t);
+  refine_kernel<<<a.B, kMergeThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 

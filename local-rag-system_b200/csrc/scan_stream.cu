@@ -21,6 +21,8 @@
 //   Within a block the warp takes R live rows at a time; every lane issues
 //   R x NJ independent 16-byte streaming loads (no L1 allocation) before the
 //   first FMA, so 16 resident warps/SM keep ~96 KB/SM in flight.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -110,6 +112,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   const int k = a.k;
   const int kpad = next_pow2(k);
   const int b0 = blockIdx.y * QB;
+  // optional indirection (exact re-run of the few queries the split-precision tensor regime could
+  // not certify): the launch covers the worst case, the device-side count says how many are real
+  const int nB = a.q_count ? min(*a.q_count, a.B) : a.B;
+  if (b0 >= nB) return;
 
   float* q_s = reinterpret_cast<float*>(smem_raw);
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(QB) * row_elems * sizeof(float));
@@ -123,8 +129,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     if (warp < QB) {
       const int b = b0 + warp;
       float ss = 0.0f;
-      if (a.normalise && b < a.B) {
-        const float* src = a.queries_raw + static_cast<size_t>(b) * a.dim;
+      if (a.normalise && b < nB) {
+        const float* src = a.queries_raw + static_cast<size_t>(a.q_index ? a.q_index[b] : b) * a.dim;
         for (int e = lane; e < a.dim; e += 32) { const float x = src[e]; ss = fmaf(x, x, ss); }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
@@ -137,9 +143,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     int qb = idx / row_elems, e = idx - qb * row_elems;
     int b = b0 + qb;
     float val = 0.0f;
-    if (b < a.B) {
+    if (b < nB) {
       if (a.queries_raw != nullptr) {
-        val = (e < a.dim) ? a.queries_raw[static_cast<size_t>(b) * a.dim + e] * s_scale[qb] : 0.0f;
+        const int bs = a.q_index ? a.q_index[b] : b;
+        val = (e < a.dim) ? a.queries_raw[static_cast<size_t>(bs) * a.dim + e] * s_scale[qb] : 0.0f;
         if (a.round_bf16) val = __bfloat162float(__float2bfloat16_rn(val));
       } else {
         val = a.queries[static_cast<size_t>(b) * row_elems + e];
@@ -251,6 +258,15 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     }
   }
 
+  // ---- programmatic dependent launch: back-to-back queries overlap tail and head --------------
+  // Everything above only READS (corpus, bitmaps, queries).  Once this CTA is done scanning, the
+  // next launch on the stream may start filling the SMs that fall idle while the stragglers, the
+  // cross-CTA merge and the cross-GPU exchange of THIS query finish; that launch, in turn, must
+  // not write any global scratch (lists, tickets, outputs are reused between queries) before its
+  // predecessor has completed.  Both instructions are no-ops for ordinary launches.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   // ---- CTA merge: sort each query's 8 warp lists together, publish the first k -----------------
   __syncthreads();
   __shared__ int s_flag;
@@ -258,7 +274,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
 #pragma unroll 1
   for (int qb = 0; qb < QB; ++qb) {
     const int b = b0 + qb;
-    if (b >= a.B) break;
+    if (b >= nB) break;
     uint64_t* region = lists + static_cast<size_t>(qb) * kScanWarps * kpad;
     block_bitonic_sort(region, kScanWarps * kpad);
     uint64_t* out = a.partial + (static_cast<size_t>(blockIdx.x) * a.B + b) * k;
@@ -283,7 +299,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
 #pragma unroll 1
   for (int qb = 0; qb < QB; ++qb) {
     const int b = b0 + qb;
-    if (b >= a.B) break;
+    if (b >= nB) break;
     uint64_t* sorted;
     __syncthreads();
     if (k <= 64 && S <= 2 * static_cast<int>(blockDim.x)) {
@@ -385,7 +401,22 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       block_bitonic_sort(pool, kScanWarps * kpad);
       sorted = pool;
     }
+    if (a.xchg_peers != nullptr) {
+      // publish this shard's list of query b into the slot [parity][my rank] of EVERY rank's buffer
+      const int par = static_cast<int>(a.xchg_epoch & 1u);
+      for (int idx = threadIdx.x; idx < a.xchg_world * k; idx += blockDim.x) {
+        const int g = idx / k, j = idx - g * k;
+        uint64_t key = sorted[j];
+        if (key != kEmptyKey) key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+        uint64_t* dst = reinterpret_cast<uint64_t*>(a.xchg_peers[g] + kXchgKeysOff) +
+                        (static_cast<size_t>(par) * a.xchg_world + a.xchg_rank) * a.xchg_slot_keys +
+                        static_cast<size_t>(b) * k + j;
+        st_relaxed_sys_u64(dst, key);
+      }
+      continue;
+    }
     int cnt = 0;
+    const int bs = a.q_index ? a.q_index[b] : b;      // where this query's result belongs
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
       uint64_t key = sorted[j];
       const bool valid = key != kEmptyKey;
@@ -393,7 +424,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
         cnt++;
       }
-      const size_t o = static_cast<size_t>(b) * k + j;
+      const size_t o = static_cast<size_t>(bs) * k + j;
       if (a.out_keys) a.out_keys[o] = key;
       if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
       if (a.out_dists) a.out_dists[o] = valid ? key_dist(key) : __int_as_float(0x7f800000);
@@ -403,7 +434,68 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       __syncthreads();
       if (cnt) atomicAdd(&s_total, cnt);
       __syncthreads();
-      if (threadIdx.x == 0) a.out_counts[b] = s_total;
+      if (threadIdx.x == 0) a.out_counts[bs] = s_total;
+    }
+  }
+  if (a.xchg_peers == nullptr) return;
+
+  // ---- fused all-gather + cross-shard merge over peer memory ----------------------------------
+  // Every thread's stores above are made visible system-wide before ONE flag per peer is raised;
+  // a peer that sees flag >= epoch (acquire) therefore sees the keys.  Two buffer halves (epoch
+  // parity) are enough: a rank can only start epoch e+2 after every rank delivered e+1, i.e.
+  // after every rank's kernel of epoch e (which read half e&1) has finished.
+  {
+    const int par = static_cast<int>(a.xchg_epoch & 1u);
+    const int G = a.xchg_world;
+    const size_t flag_idx = (static_cast<size_t>(par) * kXchgMaxGroups + blockIdx.y) * kXchgMaxWorld;
+    __threadfence_system();
+    __syncthreads();
+    if (static_cast<int>(threadIdx.x) < G) {
+      uint32_t* theirs = reinterpret_cast<uint32_t*>(a.xchg_peers[threadIdx.x]) + flag_idx + a.xchg_rank;
+      st_release_sys_u32(theirs, a.xchg_epoch);
+      const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.xchg_peers[a.xchg_rank]) + flag_idx + threadIdx.x;
+      const unsigned long long t0 = global_timer_ns();
+      while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - a.xchg_epoch) < 0) {
+        if (global_timer_ns() - t0 > 4000000000ull) {     // 4 s: a peer never launched; flag it, do not hang the GPU
+          atomicOr(reinterpret_cast<unsigned int*>(a.xchg_peers[a.xchg_rank] + kXchgStatusOff), 1u + threadIdx.x);
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    const uint64_t* slots = reinterpret_cast<const uint64_t*>(a.xchg_peers[a.xchg_rank] + kXchgKeysOff) +
+                            static_cast<size_t>(par) * G * a.xchg_slot_keys;
+    // one warp per query: lane g walks shard g's ascending list; k rounds of warp-min
+    for (int qb = warp; qb < QB; qb += kScanWarps) {
+      const int b = b0 + qb;
+      if (b >= nB) break;
+      const uint64_t* lst = slots + static_cast<size_t>(lane < G ? lane : 0) * a.xchg_slot_keys + static_cast<size_t>(b) * k;
+      int pos = 0;
+      uint64_t cur = (lane < G) ? ld_relaxed_sys_u64(lst) : kEmptyKey;
+      int cnt = 0;
+      for (int r = 0; r < k; ++r) {
+        uint64_t m = cur;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const uint64_t o = shfl_u64(m, lane ^ off);
+          m = o < m ? o : m;
+        }
+        const bool valid = m != kEmptyKey;
+        if (lane == 0) {
+          const size_t o = static_cast<size_t>(b) * k + r;
+          if (a.out_keys) a.out_keys[o] = m;
+          if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(m)) : -1;
+          if (a.out_dists) a.out_dists[o] = valid ? key_dist(m) : __int_as_float(0x7f800000);
+        }
+        if (valid) {
+          cnt++;
+          if (cur == m) {                        // global rows are unique: exactly one lane advances
+            pos++;
+            cur = (pos < k) ? ld_relaxed_sys_u64(lst + pos) : kEmptyKey;
+          }
+        }
+      }
+      if (lane == 0 && a.out_counts) a.out_counts[b] = cnt;
     }
   }
 }
@@ -424,25 +516,30 @@ size_t scan_total_smem(int QB, int row_elems, int k, int grid_x, int* merge_cap)
   return need;
 }
 
+template <typename Kern>
+cudaError_t launch_pdl(Kern kern, const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  static const bool pdl = !(getenv("RAG_B200_PDL") && atoi(getenv("RAG_B200_PDL")) == 0);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kScanThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
 template <bool BF16, int QB, int NJ, int R, int LPR>
 cudaError_t launch_one(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  cudaError_t e;
-  if (a.l2) {
-    auto kern = scan_stream_kernel<BF16, QB, NJ, R, true, LPR>;
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return e;
-    }
-    kern<<<grid, kScanThreads, smem, st>>>(a);
-  } else {
-    auto kern = scan_stream_kernel<BF16, QB, NJ, R, false, LPR>;
-    if (smem > 48 * 1024) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      if (e != cudaSuccess) return e;
-    }
-    kern<<<grid, kScanThreads, smem, st>>>(a);
-  }
-  return cudaGetLastError();
+  if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR>, a, grid, smem, st);
+  return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR>, a, grid, smem, st);
 }
 
 template <bool BF16, int QB>

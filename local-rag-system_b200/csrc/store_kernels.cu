@@ -50,12 +50,38 @@ __global__ void __launch_bounds__(kThreads) upsert_kernel(const UpsertArgs a) {
       float x = (e < a.dim) ? src[e] * scale : 0.0f;
       stored_ss = fmaf(x, x, stored_ss);
       dst[e] = x;
+      if (a.shadow) {                  // keep the split-precision shadow in step with the row
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        a.shadow[row * 2 * a.row_elems + e] = h;
+        a.shadow[row * 2 * a.row_elems + a.row_elems + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+      }
     }
   }
   stored_ss = warp_sum(stored_ss);
+  if (lane == 0 && a.max_norm2 != nullptr) {    // non-negative floats order like their bit patterns
+    const unsigned int bits = __float_as_uint(stored_ss);
+    if (bits > *reinterpret_cast<volatile unsigned int*>(a.max_norm2))
+      atomicMax(reinterpret_cast<unsigned int*>(a.max_norm2), bits);
+  }
   if (lane == 0) {
     a.norms2[row] = stored_ss;
     atomicOr(a.live + (row >> 5), 1u << (row & 31));
+  }
+}
+
+// x = hi + lo + O(2^-18 |x|): two bf16 planes that let the tensor cores contract fp32 rows
+__global__ void __launch_bounds__(kThreads) split_rows_kernel(const float* vectors, int row_elems, int64_t row0,
+                                                             int64_t n, __nv_bfloat16* shadow) {
+  const int64_t total = n * row_elems;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / row_elems;
+    const int e = static_cast<int>(i - r * row_elems);
+    const float x = vectors[(row0 + r) * row_elems + e];
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    __nv_bfloat16* dst = shadow + (row0 + r) * 2 * row_elems;
+    dst[e] = h;
+    dst[row_elems + e] = __float2bfloat16_rn(x - __bfloat162float(h));
   }
 }
 
@@ -87,7 +113,16 @@ __global__ void __launch_bounds__(kThreads) prep_queries_kernel(const PrepArgs a
     if (a.round_bf16) x = round_bf16(x);
     n2 = fmaf(x, x, n2);
     a.q_f32[static_cast<size_t>(b) * a.row_elems + e] = x;
-    if (a.q_bf16) a.q_bf16[static_cast<size_t>(b) * a.row_elems + e] = __float2bfloat16_rn(x);
+    if (a.q_bf16) {
+      if (a.split) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        __nv_bfloat16* dst = a.q_bf16 + static_cast<size_t>(b) * 2 * a.row_elems;
+        dst[e] = h;
+        dst[a.row_elems + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+      } else {
+        a.q_bf16[static_cast<size_t>(b) * a.row_elems + e] = __float2bfloat16_rn(x);
+      }
+    }
   }
   n2 = warp_sum(n2);
   if (lane == 0 && a.q_norm2) a.q_norm2[b] = n2;
@@ -113,6 +148,16 @@ cudaError_t launch_upsert(const UpsertArgs& a, cudaStream_t st) {
   if (a.n <= 0) return cudaSuccess;
   const int64_t ctas = (a.n + kWarpsPerCta - 1) / kWarpsPerCta;
   upsert_kernel<<<static_cast<unsigned>(ctas), kThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split_rows(const float* vectors, int row_elems, int64_t row0, int64_t n, __nv_bfloat16* shadow,
+                              cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t total = n * row_elems;
+  int64_t ctas = (total + kThreads - 1) / kThreads;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  split_rows_kernel<<<static_cast<unsigned>(ctas), kThreads, 0, st>>>(vectors, row_elems, row0, n, shadow);
   return cudaGetLastError();
 }
 

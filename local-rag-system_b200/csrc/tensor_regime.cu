@@ -205,6 +205,7 @@ struct Args {
   int cpm;                       // CTAs per query tile
   int dense;                     // 1: no filter and no tombstones -> tile masks are computed, not loaded
   int prefetch;                  // L2 prefetch distance in tiles (0 = off)
+  int split_steps;               // > 0: split-precision rows [hi | lo], the first split_steps k-steps are hi
   uint64_t* partial;             // [cpm][B][k]
 };
 
@@ -532,7 +533,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           const uint64_t dstage = desc0 + static_cast<uint64_t>((s * kStageBytes) >> 4);
           const uint32_t a0 = tmem_base + static_cast<uint32_t>(ks * kMmasPerStage * 8);
           const int left = k_steps - ks * kMmasPerStage;
-          if (left >= kMmasPerStage) {
+          if (a.split_steps > 0) {
+            // fp32 store contracted as bf16 pairs: q.x ~ qh.xh + ql.xh + qh.xl  (ql.xl < 2^-18 |q||x| dropped).
+            // B k-step g of the [hi | lo] shadow row pairs with A columns of q_hi (and q_lo while g is a hi step).
+            const int g0 = ks * kMmasPerStage;
+            const int nst = left < kMmasPerStage ? left : kMmasPerStage;
+#pragma unroll 1
+            for (int j = 0; j < nst; ++j) {
+              const int g = g0 + j;
+              const uint64_t bdesc = dstage + static_cast<uint64_t>(((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4);
+              if (g < a.split_steps) {
+                umma_ts(d_tmem, tmem_base + static_cast<uint32_t>(g * 8), bdesc, kIdesc, g > 0 ? 1u : 0u);
+                umma_ts(d_tmem, tmem_base + static_cast<uint32_t>((g + a.split_steps) * 8), bdesc, kIdesc, 1u);
+              } else {
+                umma_ts(d_tmem, tmem_base + static_cast<uint32_t>((g - a.split_steps) * 8), bdesc, kIdesc, 1u);
+              }
+            }
+          } else if (left >= kMmasPerStage) {
 #pragma unroll
             for (int j = 0; j < kMmasPerStage; ++j)
               umma_ts(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4), kIdesc,
@@ -588,6 +605,7 @@ struct Layout {
   size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_merged, total;
 };
 
+// row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
 Layout make_layout(int row_elems, int B, int k, int sm_count) {
   Layout L{};
   L.n_mtiles = (B + kM - 1) / kM;
@@ -636,15 +654,29 @@ cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int cl, d
 
 struct Plan { int unused; };
 
+static bool split_enabled() {
+  static const bool on = !(getenv("RAG_B200_F32_TENSOR") && atoi(getenv("RAG_B200_F32_TENSOR")) == 0);
+  return on;
+}
+
+int candidates_kept(int dtype, int k) {
+  if (dtype == 1) return k;
+  return k <= 10 ? 16 : k + 16;      // slack for the exact re-ranking of approximately ranked rows
+}
+
 bool supported(int dtype, int row_elems, int k, int space) {
   (void)space;
-  return dtype == 1 /*bf16*/ && row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && k >= 1 && k <= 1024 &&
-         get_encode() != nullptr;
+  if (get_encode() == nullptr || k < 1) return false;
+  if (dtype == 1) return row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && k <= 1024;
+  // fp32 rows as [hi | lo] bf16: the A operand takes row_elems TMEM columns; k-steps must not straddle hi/lo
+  return split_enabled() && row_elems >= 16 && row_elems % 16 == 0 && row_elems <= kMaxKCols &&
+         candidates_kept(dtype, k) <= 1024;
 }
 
 size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count) {
-  if (dtype != 1) return 0;
-  return make_layout(row_elems, B, k, sm_count).total;
+  if (!supported(dtype, row_elems, k, 0)) return 0;
+  const int width = dtype == 1 ? row_elems : 2 * row_elems;
+  return make_layout(width, B, candidates_kept(dtype, k), sm_count).total;
 }
 
 Plan* create_plan() { return new Plan(); }
@@ -653,29 +685,34 @@ void invalidate(Plan*) {}
 
 cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* launches) {
   if (!supported(p.dtype, p.row_elems, p.k, p.space)) return cudaErrorNotSupported;
-  const Layout L = make_layout(p.row_elems, p.B, p.k, p.sm_count);
+  const bool split = (p.dtype != 1);
+  const int width = split ? 2 * p.row_elems : p.row_elems;       // bf16 elements per streamed row
+  const int kk = candidates_kept(p.dtype, p.k);
+  if (split && p.shadow == nullptr) return cudaErrorInvalidValue;
+  const Layout L = make_layout(width, p.B, kk, p.sm_count);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(p.scratch + L.off_qbf16);
   float* q_norm = reinterpret_cast<float*>(p.scratch + L.off_qnorm);
   float* q_f32 = reinterpret_cast<float*>(p.scratch + L.off_qf32);
   uint64_t* part = reinterpret_cast<uint64_t*>(p.scratch + L.off_partial);
 
   // queries: zero the padded tile rows, then normalise / round / convert
-  cudaError_t e = cudaMemsetAsync(q_bf16, 0, static_cast<size_t>(L.n_mtiles) * kM * p.row_elems * 2, st);
+  cudaError_t e = cudaMemsetAsync(q_bf16, 0, static_cast<size_t>(L.n_mtiles) * kM * width * 2, st);
   if (e != cudaSuccess) return e;
   PrepArgs pa{};
   pa.src = p.queries_raw; pa.B = p.B; pa.dim = p.dim; pa.row_elems = p.row_elems;
-  pa.normalise = (p.space == 1); pa.round_bf16 = 1;
+  pa.normalise = (p.space == 1); pa.round_bf16 = split ? 0 : 1; pa.split = split ? 1 : 0;
   pa.q_f32 = q_f32; pa.q_bf16 = q_bf16; pa.q_norm2 = q_norm;
   e = launch_prep_queries(pa, st);
   if (e != cudaSuccess) return e;
 
   // TMA descriptor over the live part of the corpus: [n_rows][row_elems] bf16, box 64 x 64, 128B swizzle
   CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(p.row_elems), static_cast<cuuint64_t>(p.n_rows)};
-  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(p.row_elems) * 2};
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(p.n_rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(width) * 2};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kNB / L.cl)};
   const cuuint32_t estride[2] = {1, 1};
-  CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(p.vectors), gdim, gstride, box,
+  CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                            const_cast<void*>(split ? static_cast<const void*>(p.shadow) : p.vectors), gdim, gstride, box,
                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
@@ -683,21 +720,24 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   Args a{};
   a.q_bf16 = q_bf16; a.q_norm2 = q_norm; a.x_norm2 = p.norms2;
   a.live = p.live; a.filter = p.filter; a.filter_words = p.filter_words;
-  a.n_rows = p.n_rows; a.row_elems = p.row_elems; a.B = p.B; a.k = p.k; a.cpm = L.cpm; a.partial = part;
+  a.n_rows = p.n_rows; a.row_elems = width; a.B = p.B; a.k = kk; a.cpm = L.cpm; a.partial = part;
+  a.split_steps = split ? p.row_elems / 16 : 0;
   a.dense = p.dense;
   a.prefetch = 0;
   if (const char* e = getenv("RAG_B200_TENSOR_PF")) a.prefetch = atoi(e);
   // lists of CTAs that never see a tile must still read as empty
-  e = cudaMemsetAsync(part, 0xFF, static_cast<size_t>(L.cpm) * p.B * p.k * 8, st);
+  e = cudaMemsetAsync(part, 0xFF, static_cast<size_t>(L.cpm) * p.B * kk * 8, st);
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm, L.n_mtiles, 1);
   const bool l2 = (p.space == 0);
-  if (p.k <= 16) e = launch_kl<16>(tmap, a, l2, L.cl, grid, st);
-  else if (p.k <= 128) e = launch_kl<128>(tmap, a, l2, L.cl, grid, st);
+  if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.cl, grid, st);
+  else if (kk <= 128) e = launch_kl<128>(tmap, a, l2, L.cl, grid, st);
   else e = launch_kl<1024>(tmap, a, l2, L.cl, grid, st);
   if (e != cudaSuccess) return e;
   out->partial = part;
   out->S = L.cpm;
+  out->k_kept = kk;
+  out->q_norm2 = q_norm;
   out->q_f32 = q_f32;
   out->merged = reinterpret_cast<uint64_t*>(p.scratch + L.off_merged);
   if (launches) *launches += 2;

@@ -10,11 +10,15 @@ namespace tensor {
 // batches larger than this go to the tensor regime when it supports the store (measured on
 // B200, 10M x 768 bf16: stream 2.24 ms @ B=2, 2.68 ms @ B=4; tensor 2.5 ms for any B <= 128)
 constexpr int kStreamMaxBatch = 3;
+// fp32 stores: the exact stream kernel shares one corpus pass between 8 queries; beyond that the
+// split-precision contraction (one pass per 128 queries + exact re-ranking) wins
+constexpr int kStreamMaxBatchF32 = 8;
 
 struct Plan;   // cached TMA descriptors etc. for one store
 
 struct Problem {
-  const void* vectors;      // [n_rows][row_elems] bf16, row-major
+  const void* vectors;      // [n_rows][row_elems] bf16 (or fp32 when `shadow` is streamed instead), row-major
+  const void* shadow;       // fp32 stores: [n_rows][hi(row_elems) | lo(row_elems)] bf16 split of the rows
   const float* norms2;      // [n_rows] |x|^2 of the stored rows (l2 space)
   int64_t n_rows;
   int row_elems, dim, dtype, space;
@@ -29,15 +33,20 @@ struct Problem {
 };
 
 bool supported(int dtype, int row_elems, int k, int space);
+// candidates the kernel keeps per query: k for bf16 stores (exact ranking of the stored values);
+// more for fp32 stores, whose rows are ranked through a bf16 hi/lo split and re-ranked exactly
+int candidates_kept(int dtype, int k);
 size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count);
 Plan* create_plan();
 void destroy_plan(Plan* p);
 void invalidate(Plan* p);     // corpus pointer / capacity changed
 struct Result {
-  const uint64_t* partial;  // [S][B][k] ascending candidate lists per query (inside `scratch`)
+  const uint64_t* partial;  // [S][B][k_kept] ascending candidate lists per query (inside `scratch`)
   int S;
+  int k_kept;               // list length: k, or k + slack when ranking was approximate (fp32 stores)
+  const float* q_norm2;     // [B] |prepared query|^2
   const float* q_f32;       // [B][row_elems] prepared queries (for the l2 refinement)
-  uint64_t* merged;         // [B][k] scratch for the merged keys before refinement
+  uint64_t* merged;         // [B][k_kept] scratch for the merged keys before refinement
 };
 // Runs prep + contraction + fused select.
 cudaError_t launch(Plan* plan, const Problem& p, cudaStream_t st, Result* out, int* launches);

@@ -145,6 +145,22 @@ class DeviceStore:
                                               flags, int(row_base), vp(out_keys_ptr), vp(out_rows_ptr),
                                               vp(out_dists_ptr), vp(out_counts_ptr), vp(stream)))
 
+    def query_fused(self, exchange: "Exchange", queries_ptr: int, B: int, k: int, out_rows_ptr: int,
+                    out_dists_ptr: int = 0, out_counts_ptr: int = 0, stream: int = 0, mask_slot: int = -1,
+                    row_base: int = 0, regime: str = "auto"):
+        """Multi-GPU search in ONE launch: shard scan, all-gather of the B x k keys over
+        NVLink peer memory and the cross-shard merge are fused (see Exchange).  Every rank
+        must make the same call; the GLOBAL result lands on every rank."""
+        flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
+        vp = lambda p: C.c_void_p(int(p)) if p else None
+        N.check(self._lib.rag_store_query_fused_dev(self._h, exchange.handle, int(B), C.c_void_p(int(queries_ptr)),
+                                                    int(k), int(mask_slot), flags, int(row_base), vp(out_rows_ptr),
+                                                    vp(out_dists_ptr), vp(out_counts_ptr), vp(stream)))
+
+    def fused_ok(self, exchange: "Exchange", B: int, k: int, regime: str = "auto") -> bool:
+        flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
+        return bool(self._lib.rag_store_fused_ok(self._h, exchange.handle, int(B), int(k), flags))
+
     def last_query_info(self):
         ms, regime, launches = C.c_float(), C.c_int32(), C.c_int32()
         N.check(self._lib.rag_store_last_query_info(self._h, C.byref(ms), C.byref(regime), C.byref(launches)))
@@ -159,3 +175,43 @@ def merge_keys_device(device: int, G: int, B: int, k: int, keys_ptr: int, out_ke
     vp = lambda p: C.c_void_p(int(p)) if p else None
     N.check(lib.rag_merge_keys_dev(int(device), int(G), int(B), int(k), vp(keys_ptr), vp(out_keys_ptr),
                                    vp(out_rows_ptr), vp(out_dists_ptr), vp(out_counts_ptr), vp(stream)))
+
+
+class Exchange:
+    """This rank's peer-mapped exchange buffer for the fused multi-GPU search
+    (include/rag_b200.h, "fused cross-shard exchange").  `all_gather_bytes` is any
+    callable that takes this rank's 64-byte handle and returns the world's handles
+    concatenated in rank order (torch.distributed in sharded.py)."""
+
+    def __init__(self, device: int, rank: int, world: int, all_gather_bytes, slot_keys: int = 8192):
+        self._lib = N.load()
+        h = C.c_void_p()
+        N.check(self._lib.rag_exchange_create(int(device), int(rank), int(world), int(slot_keys), C.byref(h)))
+        self._h = h
+        self.rank, self.world, self.slot_keys = rank, world, slot_keys
+        mine = C.create_string_buffer(N.EXCHANGE_HANDLE_BYTES)
+        N.check(self._lib.rag_exchange_handle(self._h, mine))
+        everyone = bytes(all_gather_bytes(mine.raw))
+        if len(everyone) != world * N.EXCHANGE_HANDLE_BYTES:
+            raise ValueError("all_gather_bytes must return world x 64 bytes")
+        N.check(self._lib.rag_exchange_connect(self._h, everyone))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def timed_out(self) -> bool:
+        v = C.c_int32()
+        N.check(self._lib.rag_exchange_status(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rag_exchange_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -5,22 +5,31 @@ is split row-wise into contiguous shards; rank g owns global rows
 [g * stride, g * stride + rows_g).  A query batch is replicated to every rank,
 each rank runs the shard-local scan + fused top-k (no data-path collective),
 and the only exchange is one all-gather of B x k 64-bit candidate keys per
-rank (80 B per rank for B=1, k=10) followed by the merge kernel.  Because keys
-carry global rows, the merged result is bit-identical to what a single store
-holding the whole corpus returns -- ties included.
+rank (80 B per rank for B=1, k=10) followed by a merge.  Because keys carry
+global rows, the merged result is bit-identical to what a single store holding
+the whole corpus returns -- ties included.
+
+Two implementations of the exchange:
+  * fused (small batches, the latency-bound case): the scan kernel's last CTA
+    stores the shard's keys into every rank's peer-mapped buffer over NVLink,
+    raises a flag, waits for the others and merges -- ONE launch per batch per
+    GPU and no collective call (engine.Exchange, csrc/scan_stream.cu);
+  * NCCL all_gather_into_tensor + the merge kernel (large batches / tensor
+    regime, where the exchange is bandwidth- not latency-bound).
 
 torch is used for what it is good at here: device buffers, streams and the
 process group.  The scan, select and merge are the engine's own kernels.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from .engine import DeviceStore, merge_keys_device
+from .engine import DeviceStore, Exchange, merge_keys_device
 
 
 def shard_plan(total_rows: int, world: int) -> Tuple[int, list]:
@@ -49,10 +58,29 @@ class ShardedSearcher:
     """Search front-end of one rank.  Every rank must call search*() with the
     same queries (the query batch is replicated)."""
 
-    def __init__(self, store: DeviceStore, rank: int = 0, world: int = 1, row_base: int = 0, group=None):
+    def __init__(self, store: DeviceStore, rank: int = 0, world: int = 1, row_base: int = 0, group=None,
+                 fused_exchange: bool = True):
         self.store, self.rank, self.world, self.row_base, self.group = store, rank, world, int(row_base), group
         self.device = torch.device("cuda", store.device)
         self._buf = {}
+        self.exchange: Optional[Exchange] = None
+        self.last_path = None
+        if world > 1 and fused_exchange and os.environ.get("RAG_B200_FUSED_EXCHANGE", "1") != "0":
+            self.exchange = Exchange(store.device, rank, world, self._all_gather_bytes)
+
+    def _all_gather_bytes(self, mine: bytes) -> bytes:
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)
+        out = torch.empty(self.world * t.numel(), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)
+        return out.cpu().numpy().tobytes()
+
+    def close(self):
+        if self.exchange is not None:
+            if self.world > 1:
+                torch.cuda.synchronize(self.device)
+                dist.barrier(group=self.group)     # nobody unmaps while a peer may still store into it
+            self.exchange.close()
+            self.exchange = None
 
     def _buffers(self, B: int, k: int):
         key = (B, k)
@@ -84,6 +112,13 @@ class ShardedSearcher:
                                     row_base=self.row_base, regime=regime, out_rows_ptr=b["rows"].data_ptr(),
                                     out_dists_ptr=b["dists"].data_ptr(), out_counts_ptr=b["counts"].data_ptr())
             return b["rows"], b["dists"], b["counts"]
+        if self.exchange is not None and self.store.fused_ok(self.exchange, B, k, regime):
+            self.store.query_fused(self.exchange, q_dev.data_ptr(), B, k, b["rows"].data_ptr(), b["dists"].data_ptr(),
+                                   b["counts"].data_ptr(), stream=stream, mask_slot=mask_slot,
+                                   row_base=self.row_base, regime=regime)
+            self.last_path = "fused"
+            return b["rows"], b["dists"], b["counts"]
+        self.last_path = "nccl"
         self.store.query_device(q_dev.data_ptr(), B, k, b["local"].data_ptr(), stream=stream,
                                 mask_slot=mask_slot, row_base=self.row_base, regime=regime)
         gathered = exchange_candidates(b["local"], self.world, self.group)

@@ -326,13 +326,124 @@ def test_auto_regime_switches_on_batch_size():
         assert st.last_query_info()["regime"] == "stream"
         st.query(x[:64], 5)
         assert st.last_query_info()["regime"] == "tensor"
-        f32.query(x[:64], 5)                               # fp32 stores stay on the exact fp32 stream kernel
+        f32.query(x[:8], 5)                                # fp32: 8 queries share one exact stream pass
         assert f32.last_query_info()["regime"] == "stream"
-        with pytest.raises(ValueError):
-            f32.query(x[:4], 5, regime="tensor")
+        f32.query(x[:64], 5)                               # beyond that: split-precision contraction + exact re-rank
+        assert f32.last_query_info()["regime"] == "tensor"
+        odd = DeviceStore(100, "f32", "cosine")            # hi/lo k-steps need dim % 16 == 0: stays on the stream kernel
+        try:
+            odd.upsert(unit_rows(500, 100, 2))
+            odd.query(unit_rows(64, 100, 3), 5)
+            assert odd.last_query_info()["regime"] == "stream"
+            with pytest.raises(ValueError):
+                odd.query(unit_rows(4, 100, 3), 5, regime="tensor")
+        finally:
+            odd.close()
     finally:
         st.close()
         f32.close()
+
+
+# ------------------------------------------------------------------------------------
+# tensor regime on fp32 stores: rows contracted as bf16 hi/lo pairs (3 MMAs per k-step),
+# k + slack candidates re-ranked exactly from the fp32 rows, uncertifiable queries re-run
+# on the exact stream kernel.  Held to the fp32 bar, not the bf16 one.
+# ------------------------------------------------------------------------------------
+SPLIT_CASES = [
+    # space, n, dim, B, k
+    ("cosine", 5000, 384, 16, 10),
+    ("l2", 3000, 384, 130, 16),           # raw gaussian rows (|x|^2 ~ 384): the error bound scales with the norms
+    ("ip", 4099, 128, 128, 10),
+    ("cosine", 2000, 64, 20, 100),
+    ("l2", 1000, 16, 9, 5),               # one k-step of hi, one of lo
+    ("cosine", 37, 48, 12, 10),           # fewer rows than one tile
+    ("cosine", 20000, 384, 1024, 10),     # config 2's batch shape on a small corpus
+]
+
+
+@pytest.mark.parametrize("space,n,dim,B,k", SPLIT_CASES)
+def test_fp32_tensor_regime_matches_oracle(space, n, dim, B, k):
+    rng = np.random.default_rng(n * 5 + dim + B + k)
+    x = rng.standard_normal((n, dim)).astype(np.float32) if space != "cosine" else unit_rows(n, dim, n)
+    q = rng.standard_normal((B, dim)).astype(np.float32)
+    q[0] = x[n // 2] + 0.01 * rng.standard_normal(dim).astype(np.float32)
+    st = DeviceStore(dim, "f32", space)
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        assert st.last_query_info()["regime"] == "tensor"
+        check_against_oracle(space, "f32", stored, q, k, rows, dists, counts, min_recall=1.0)
+        r2, d2, c2 = st.query(q, k, regime="stream")
+        assert np.array_equal(c2, counts)
+        assert np.allclose(dists, d2, rtol=1e-5, atol=2e-6)
+    finally:
+        st.close()
+
+
+def test_fp32_tensor_regime_near_ties_are_decided_exactly():
+    """More near-identical rows than the candidate slack: the approximate ranking cannot tell
+    them apart, the guard must notice and the exact stream kernel must decide -- the result is
+    then the stream regime's, bit for bit."""
+    n, dim, k, B = 4000, 384, 10, 24
+    x = unit_rows(n, dim, 31)
+    rng = np.random.default_rng(32)
+    base = x[100].copy()
+    cluster = np.arange(1000, 1060)
+    x[cluster] = base[None, :] + 2e-7 * rng.standard_normal((cluster.size, dim)).astype(np.float32)
+    q = unit_rows(B, dim, 33)
+    q[3] = base
+    q[17] = base + 1e-7 * rng.standard_normal(dim).astype(np.float32)
+    st = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        rt, dt, ct = st.query(q, k, regime="tensor")
+        rs, ds, cs = st.query(q, k, regime="stream")
+        assert np.array_equal(rt[[3, 17]], rs[[3, 17]]) and np.array_equal(dt[[3, 17]], ds[[3, 17]])
+        assert np.array_equal(rt, rs) and np.allclose(dt, ds, rtol=1e-5, atol=2e-6)
+        check_against_oracle("cosine", "f32", stored, q, k, rt, dt, ct, min_recall=1.0)
+    finally:
+        st.close()
+
+
+def test_fp32_tensor_regime_shadow_follows_writes():
+    """The hi/lo shadow is built on first use, kept in step by in-place upserts and appends,
+    dropped when the store grows and rebuilt; tombstones and `where` masks apply as usual."""
+    n, dim, k, B = 3000, 128, 10, 40
+    x = unit_rows(n, dim, 41)
+    q = unit_rows(B, dim, 42)
+    rng = np.random.default_rng(43)
+    st = DeviceStore(dim, "f32", "l2", capacity_hint=4096)
+    try:
+        st.upsert(x)
+        rows, dists, counts = st.query(q, k, regime="tensor")           # builds the shadow
+        check_against_oracle("l2", "f32", x, q, k, rows, dists, counts)
+        winners = rows[:, 0].copy()
+        fresh = unit_rows(len(winners), dim, 44)
+        st.upsert(fresh, rows=winners)                                   # overwrite the winners in place
+        x[winners] = fresh
+        more = unit_rows(500, dim, 45)                                   # append within capacity
+        st.upsert(more)
+        x = np.vstack([x, more])
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        check_against_oracle("l2", "f32", x, q, k, rows, dists, counts)
+        big = unit_rows(3000, dim, 46)                                   # grows the store: shadow is rebuilt
+        st.upsert(big)
+        x = np.vstack([x, big])
+        assert st.capacity() > 4096
+        live = np.ones(x.shape[0], bool)
+        dead = rng.choice(x.shape[0], 300, replace=False)
+        st.delete(dead)
+        live[dead] = False
+        passing = rng.random(x.shape[0]) < 0.2
+        st.set_mask(0, passing)
+        rows, dists, counts = st.query(q, k, mask_slot=0, regime="tensor")
+        check_against_oracle("l2", "f32", x, q, k, rows, dists, counts, valid=live & passing)
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        check_against_oracle("l2", "f32", x, q, k, rows, dists, counts, valid=live)
+    finally:
+        st.close()
 
 
 def test_tensor_regime_large_properties():
