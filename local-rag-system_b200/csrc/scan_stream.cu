@@ -112,6 +112,12 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   const int k = a.k;
   const int kpad = next_pow2(k);
   const int b0 = blockIdx.y * QB;
+  // ---- programmatic dependent launch, part 1 -----------------------------------------------------
+  // Allow the NEXT launch on the stream to be scheduled as soon as every CTA of this one has
+  // started: its CTAs then take over each SM slot the moment one of ours exits, so back-to-back
+  // queries overlap the stragglers, the cross-CTA merge and the cross-GPU exchange of one query
+  // with the scan of the next (worth ~7 % at a 1.9 GB shard).  See part 2 for the other half.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // optional indirection (exact re-run of the few queries the split-precision tensor regime could
   // not certify): the launch covers the worst case, the device-side count says how many are real
   const int nB = a.q_count ? min(*a.q_count, a.B) : a.B;
@@ -177,94 +183,177 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   const int64_t nblk = (a.n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   const int64_t wstride = static_cast<int64_t>(gridDim.x) * kScanWarps;
 
-  for (int64_t blk = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; blk < nblk; blk += wstride) {
-    uint32_t m = __ldg(a.live + blk);
-    if (a.filter != nullptr) m &= (blk < a.filter_words) ? __ldg(a.filter + blk) : 0u;
-    const uint4* bbase = vec + static_cast<size_t>(blk) * kRowsPerBlock * cpr;
-    while (m) {
-      int r[R];                                      // this lane's row in each slot (-1: none)
+  // One step of the scan: the R row slots `r[]` (row index relative to `base`, -1 = empty slot; with
+  // sub-warp rows each lane group carries its own row per slot) are loaded, contracted with the
+  // queries and offered to the top-k lists.  `row0` = store row of `base`.
+  auto process = [&](const uint4* base, int64_t row0, const int (&r)[R]) {
+    float acc[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[i] = 0.0f;
+
+    if constexpr (NJ > 0) {
+      uint4 v[R][NJ];
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        r[i] = -1;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int bit = m ? (__ffs(m) - 1) : -1;
-          m &= (m - 1);
-          if (G == 1 || g == grp) r[i] = bit;
-        }
-      }
-      float acc[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) acc[i] = 0.0f;
-
-      if constexpr (NJ > 0) {
-        uint4 v[R][NJ];
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            v[i][j] = (r[i] >= 0) ? ldg_stream(bbase + static_cast<size_t>(r[i]) * cpr + j * LPR + sl)
-                                  : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          const int c = j * LPR + sl;
-#pragma unroll
-          for (int qb = 0; qb < QB; ++qb) {
-            const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
-            float4 qa = qrow[c];
-            float4 qh = BF16 ? qrow[cpr + c] : qa;
-#pragma unroll
-            for (int i = 0; i < R; ++i) acc[i * QB + qb] = chunk_acc<BF16, L2>(acc[i * QB + qb], v[i][j], qa, qh);
-          }
-        }
-      } else {
-        for (int c = lane; c < cpr; c += 32) {
-          uint4 v[R];
-#pragma unroll
-          for (int i = 0; i < R; ++i)
-            v[i] = (r[i] >= 0) ? ldg_stream(bbase + static_cast<size_t>(r[i]) * cpr + c) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-          for (int qb = 0; qb < QB; ++qb) {
-            const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
-            float4 qa = qrow[c];
-            float4 qh = BF16 ? qrow[cpr + c] : qa;
-#pragma unroll
-            for (int i = 0; i < R; ++i) acc[i * QB + qb] = chunk_acc<BF16, L2>(acc[i * QB + qb], v[i], qa, qh);
-          }
+          v[i][j] = (r[i] >= 0) ? ldg_stream(base + static_cast<size_t>(r[i]) * cpr + j * LPR + sl)
+                                : make_uint4(0u, 0u, 0u, 0u);
         }
       }
-
-      const float total = Fold<V, LPR / 2>::run(acc, lane);
-      int myr = r[0];
 #pragma unroll
-      for (int i = 1; i < R; ++i) myr = (my_i == i) ? r[i] : myr;
-      const float dist = L2 ? total : (1.0f - total);
-      const uint64_t key = make_key(dist, static_cast<uint32_t>(blk * kRowsPerBlock + myr));
-      uint32_t bal = __ballot_sync(0xffffffffu, rep && (myr >= 0) && (key < my_tau));
-      while (bal) {
-        const int src = __ffs(bal) - 1;
-        bal &= (bal - 1);
-        const uint64_t ck = shfl_u64(key, src);
-        const int sidx = (src & (LPR - 1)) >> SHIFT;
-        const int cqb = sidx - (sidx / QB) * QB;
-        uint64_t* L = lists + (static_cast<size_t>(cqb) * kScanWarps + warp) * kpad;
-        if (ck < L[k - 1]) {   // tau may have tightened since the ballot
-          warp_list_insert(L, k, ck, lane);
-          if (my_qb == cqb) my_tau = L[k - 1];
+      for (int j = 0; j < NJ; ++j) {
+        const int c = j * LPR + sl;
+#pragma unroll
+        for (int qb = 0; qb < QB; ++qb) {
+          const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
+          float4 qa = qrow[c];
+          float4 qh = BF16 ? qrow[cpr + c] : qa;
+#pragma unroll
+          for (int i = 0; i < R; ++i) acc[i * QB + qb] = chunk_acc<BF16, L2>(acc[i * QB + qb], v[i][j], qa, qh);
         }
+      }
+    } else {
+      for (int c = lane; c < cpr; c += 32) {
+        uint4 v[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          v[i] = (r[i] >= 0) ? ldg_stream(base + static_cast<size_t>(r[i]) * cpr + c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int qb = 0; qb < QB; ++qb) {
+          const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
+          float4 qa = qrow[c];
+          float4 qh = BF16 ? qrow[cpr + c] : qa;
+#pragma unroll
+          for (int i = 0; i < R; ++i) acc[i * QB + qb] = chunk_acc<BF16, L2>(acc[i * QB + qb], v[i], qa, qh);
+        }
+      }
+    }
+
+    const float total = Fold<V, LPR / 2>::run(acc, lane);
+    int myr = r[0];
+#pragma unroll
+    for (int i = 1; i < R; ++i) myr = (my_i == i) ? r[i] : myr;
+    const float dist = L2 ? total : (1.0f - total);
+    const uint64_t key = make_key(dist, static_cast<uint32_t>(row0 + myr));
+    uint32_t bal = __ballot_sync(0xffffffffu, rep && (myr >= 0) && (key < my_tau));
+    while (bal) {
+      const int src = __ffs(bal) - 1;
+      bal &= (bal - 1);
+      const uint64_t ck = shfl_u64(key, src);
+      const int sidx = (src & (LPR - 1)) >> SHIFT;
+      const int cqb = sidx - (sidx / QB) * QB;
+      uint64_t* L = lists + (static_cast<size_t>(cqb) * kScanWarps + warp) * kpad;
+      if (ck < L[k - 1]) {   // tau may have tightened since the ballot
+        warp_list_insert(L, k, ck, lane);
+        if (my_qb == cqb) my_tau = L[k - 1];
+      }
+    }
+  };
+
+  if (a.filter == nullptr) {
+    // ---- dense walk: one 32-row block (one bitmap word) per warp step ---------------------------
+    for (int64_t blk = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; blk < nblk; blk += wstride) {
+      uint32_t m = __ldg(a.live + blk);
+      const uint4* bbase = vec + static_cast<size_t>(blk) * kRowsPerBlock * cpr;
+      while (m) {
+        int r[R];                                      // this lane's row in each slot (-1: none)
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          r[i] = -1;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int bit = m ? (__ffs(m) - 1) : -1;
+            m &= (m - 1);
+            if (G == 1 || g == grp) r[i] = bit;
+          }
+        }
+        process(bbase, blk * kRowsPerBlock, r);
+      }
+    }
+  } else {
+    // ---- filtered walk (`where` bitmap): gather the passing rows of a 256-row chunk ------------
+    // With a selective filter most 32-row blocks hold 0-3 passing rows; walking them block by
+    // block leaves the row slots (= the loads in flight) mostly empty and pays one dependent
+    // bitmap load per block.  Here lanes 0..7 fetch the 8 bitmap words of a chunk at once (the
+    // next chunk's words are requested before this one is processed), a warp scan ranks the set
+    // bits, and every step fills all R x G slots with the next passing rows of the chunk.
+    constexpr int CW = 8;                               // bitmap words per chunk
+    constexpr int kGatherMaxRows = 64;                  // gather when <= 25 % of the chunk's rows pass
+    const int64_t nchunk = (nblk + CW - 1) / CW;
+    auto fetch_words = [&](int64_t chunk) -> uint32_t {
+      const int64_t w = chunk * CW + lane;
+      if (lane >= CW || chunk >= nchunk || w >= nblk) return 0u;
+      const uint32_t f = (w < a.filter_words) ? __ldg(a.filter + w) : 0u;
+      return f ? (f & __ldg(a.live + w)) : 0u;
+    };
+    int64_t chunk = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp;
+    uint32_t next_word = fetch_words(chunk);
+    for (; chunk < nchunk; chunk += wstride) {
+      const uint32_t word = next_word;
+      next_word = fetch_words(chunk + wstride);
+      const int pop = __popc(word);
+      int incl = pop;
+#pragma unroll
+      for (int off = 1; off < CW; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+      }
+      const int T = __shfl_sync(0xffffffffu, incl, CW - 1);   // lanes >= CW hold word = 0
+      if (lane >= CW) incl = T;
+      const int excl = incl - pop;
+      const uint4* cbase = vec + static_cast<size_t>(chunk) * (CW * kRowsPerBlock) * cpr;
+      if (T > kGatherMaxRows) {
+        // well-filled chunk: block by block as in the dense walk (cheaper row selection, rows
+        // adjacent in memory), with the bitmap words already in registers
+#pragma unroll 1
+        for (int w = 0; w < CW; ++w) {
+          uint32_t m = __shfl_sync(0xffffffffu, word, w);
+          const uint4* bbase = cbase + static_cast<size_t>(w) * kRowsPerBlock * cpr;
+          while (m) {
+            int r[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              r[i] = -1;
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const int bit = m ? (__ffs(m) - 1) : -1;
+                m &= (m - 1);
+                if (G == 1 || g == grp) r[i] = bit;
+              }
+            }
+            process(bbase, (chunk * CW + w) * kRowsPerBlock, r);
+          }
+        }
+        continue;
+      }
+      for (int j0 = 0; j0 < T; j0 += R * G) {
+        int r[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          r[i] = -1;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const int j = j0 + i * G + g;               // rank of the passing row that goes into slot (i, g)
+            int row = -1;
+            if (j < T) {
+              const int wl = __popc(__ballot_sync(0xffffffffu, incl <= j));   // word holding the j-th set bit
+              const int nth = j - __shfl_sync(0xffffffffu, excl, wl);
+              const uint32_t wd = __shfl_sync(0xffffffffu, word, wl);
+              row = wl * kRowsPerBlock + static_cast<int>(__fns(wd, 0u, nth + 1));
+            }
+            if (G == 1 || g == grp) r[i] = row;
+          }
+        }
+        process(cbase, chunk * (CW * kRowsPerBlock), r);
       }
     }
   }
 
-  // ---- programmatic dependent launch: back-to-back queries overlap tail and head --------------
-  // Everything above only READS (corpus, bitmaps, queries).  Once this CTA is done scanning, the
-  // next launch on the stream may start filling the SMs that fall idle while the stragglers, the
-  // cross-CTA merge and the cross-GPU exchange of THIS query finish; that launch, in turn, must
-  // not write any global scratch (lists, tickets, outputs are reused between queries) before its
-  // predecessor has completed.  Both instructions are no-ops for ordinary launches.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // ---- programmatic dependent launch, part 2 -----------------------------------------------------
+  // Everything above only READ (corpus, bitmaps, queries).  From here on the kernel writes global
+  // scratch that is reused between queries (lists, tickets, outputs): wait until the previous
+  // launch on the stream has completed.  A no-op for ordinary launches.
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- CTA merge: sort each query's 8 warp lists together, publish the first k -----------------

@@ -49,17 +49,26 @@ constexpr int kNB = 64;              // corpus rows per tile (MMA N)
 constexpr int kAtomK = 64;           // bf16 elements per 128-byte swizzle atom row
 constexpr int kAtomsPerStage = 4;
 constexpr int kStageK = kAtomK * kAtomsPerStage;      // 256 K elements per pipeline stage
-constexpr int kAtomBytes = kNB * kAtomK * 2;          // 8 KB
-constexpr int kStageBytes = kAtomsPerStage * kAtomBytes;   // 32 KB
-constexpr int kStages = 7;                             // 224 KB in flight per SM
+// shared-memory ring geometry.  MODE 0 (one CTA) and 1 (multicast pair): a stage holds all 64 rows of
+// a tile (4 atoms x 8 KB = 32 KB, 7 stages).  MODE 2 (cta_group::2 pair): each CTA of the pair holds
+// only ITS 32 rows of every tile (4 atoms x 4 KB = 16 KB, 14 stages); the pair's tensor cores share
+// the two halves, which halves the shared-memory traffic per SM.
+template <int MODE> struct Ring {
+  static constexpr int kRows = (MODE == 2) ? kNB / 2 : kNB;
+  static constexpr int kAtomBytes = kRows * kAtomK * 2;
+  static constexpr int kStageBytes = kAtomsPerStage * kAtomBytes;
+  static constexpr int kStages = (MODE == 2) ? 14 : 7;      // 224 KB in flight per SM either way
+};
+constexpr int kRingBytes = 7 * kAtomsPerStage * kNB * kAtomK * 2;
 constexpr int kPrefetchTiles = 4;                      // L2 prefetch distance, in this CTA's tiles
 constexpr int kMmasPerStage = kStageK / 16;            // 16
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kMaxKCols = 384;       // A operand: up to 768 bf16 per query
+constexpr int kMaxAccBufs = 4;
 constexpr int kAccCols = kNB;        // fp32 accumulator columns per buffer
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/;
 
 // ---- PTX wrappers -------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -158,6 +167,43 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(mask) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// load into THIS CTA's shared memory, complete_tx on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem, both CTAs] (+)= A[tmem, 128 rows per CTA] . B[smem, kNB/2 rows per CTA]^T, issued by the leader only
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -191,6 +237,9 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = kNB
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kNB >> 3) << 17) |
                             (static_cast<uint32_t>(kM >> 4) << 24);
+// the pair's instruction: M = 256 (128 rows in each CTA's tensor memory)
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kNB >> 3) << 17) |
+                                (static_cast<uint32_t>((2 * kM) >> 4) << 24);
 
 struct Args {
   const __nv_bfloat16* q_bf16;   // [n_mtiles*128][row_elems] prepared queries, zero rows beyond B
@@ -205,6 +254,7 @@ struct Args {
   int cpm;                       // CTAs per query tile
   int dense;                     // 1: no filter and no tombstones -> tile masks are computed, not loaded
   int prefetch;                  // L2 prefetch distance in tiles (0 = off)
+  int nbuf;                      // accumulator buffers in tensor memory (2 or 4)
   int split_steps;               // > 0: split-precision rows [hi | lo], the first split_steps k-steps are hi
   uint64_t* partial;             // [cpm][B][k]
 };
@@ -284,8 +334,18 @@ struct TopList {
 // the same corpus tiles; each loads 1/CL of every tile and TMA-multicasts it to all of
 // them, so L2 -> SM traffic per CTA drops by CL (L2 bandwidth ~ HBM bandwidth on this chip,
 // and it is what bounds the unicast version at ~0.9 PFLOP/s).
-template <int KL, bool L2, int CL>
+// MODE 2 -- cta_group::2: the same two CTAs form an MMA pair instead.  Each CTA loads ITS 32 rows of a
+// tile into its own shared memory only; the leader (cluster rank 0) issues one M = 256 MMA per k-step
+// for both (each tensor core contracts its own 128 queries with the 64 rows held by the pair), so a
+// corpus byte is written to and read from shared memory once per PAIR -- half the per-SM traffic of
+// the multicast scheme (which at 64 B/clk in + 64 B/clk out sat at the SM's shared-memory limit).
+template <int KL, bool L2, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
+  constexpr int CL = (MODE == 0) ? 1 : 2;
+  constexpr bool PAIR = (MODE == 2);
+  constexpr int kStages = Ring<MODE>::kStages;
+  constexpr int kStageBytes = Ring<MODE>::kStageBytes;
+  constexpr int kAtomBytes = Ring<MODE>::kAtomBytes;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;             // 1024-byte aligned stage ring
@@ -294,14 +354,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto accf_bar = [&](int b) { return bar_base + 8u * (2 * kStages + b); };
-  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * kStages + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * kStages + kMaxAccBufs + b); };
+  const uint32_t aready_bar = bar_base + 8u * (2 * kStages + 2 * kMaxAccBufs);     // PAIR: both CTAs' queries are in tensor memory
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 2 * kMaxAccBufs + 1);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int mt = blockIdx.y;                 // query tile
-  const int cj = blockIdx.x;                 // position among the CTAs of this query tile
+  // clusters of CL CTAs lie along x (a cta_group::2 pair must): x = cj * CL + rank, y = group of CL query tiles
+  const int mt = static_cast<int>(blockIdx.y) * CL + static_cast<int>(blockIdx.x % CL);   // query tile
+  const int cj = static_cast<int>(blockIdx.x / CL);   // position among the CTAs of this query tile
   const int64_t n_tiles = (a.n_rows + kNB - 1) / kNB;
   const int kcols = ((a.row_elems + 15) / 16) * 8;         // TMEM columns of the A operand
   const int k_steps = (a.row_elems + 15) / 16;             // MMAs per tile
@@ -309,13 +371,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
-    for (int b = 0; b < 2; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), 4); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), PAIR ? 1 : CL); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), PAIR ? 8 : 4); }
+    mbar_init(aready_bar, 8);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
@@ -324,7 +387,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(kMaxKCols);   // accumulators after the A columns
+  // accumulator ring at the top of tensor memory: 2 x 64 columns behind a 768-wide A operand, 4 x 64 when
+  // the queries leave room (D <= 512).  With two buffers the hand-off chain  MMA done -> commit -> epilogue
+  // tcgen05.ld -> arrive -> next MMA  has to fit inside ONE tile's MMA time (768 cycles at D = 384), and it
+  // does not -- least of all across a CTA pair; four buffers give it three tiles.
+  const int nbuf = a.nbuf;
+  const int nbuf_log2 = (nbuf == 4) ? 2 : 1;
+  const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(kTmemCols - nbuf * kAccCols);
 
   // Walks this CTA's corpus tiles (cj, cj + cpm, ...) and yields the ones with at least one
   // live & filter-passing row.  Mask words of the NEXT tile are requested one step ahead so
@@ -381,7 +450,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       tmem_wait_st();
       tc_fence_before();
     }
-    asm volatile("bar.sync 1, 160;" ::: "memory");   // epilogue warps (128) + MMA warp (32): A operand is in TMEM
+    if constexpr (PAIR) {          // the leader's MMA warp needs BOTH CTAs' queries in place
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(aready_bar, 0));
+    } else {
+      asm volatile("bar.sync 1, 160;" ::: "memory");   // epilogue warps (128) + MMA warp (32): A operand is in TMEM
+    }
 
     TopList<KL> top;
     top.init();
@@ -395,8 +469,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     int64_t t;
     uint32_t w0, w1;
     while (walk.next(t, w0, w1)) {                   // tiles with no passing row are skipped by every role
-      const int buf = it & 1;
-      const uint32_t par = (it >> 1) & 1;
+      const int buf = it & (nbuf - 1);
+      const uint32_t par = (it >> nbuf_log2) & 1;
       ++it;
       float xn0 = 0.0f, xn1 = 0.0f;
       if constexpr (L2) {
@@ -415,7 +489,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acce_bar(buf));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(acce_bar(buf), 0));   // the leader issues for both
+        else mbar_arrive(acce_bar(buf));
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t* v = vv[half];
@@ -494,14 +571,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         int atoms = (a.row_elems - k0 + kAtomK - 1) / kAtomK;       // atoms that hold real columns
         atoms = atoms > kAtomsPerStage ? kAtomsPerStage : atoms;
         if (elect_one()) {
-          mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(atoms) * kAtomBytes);   // bytes from all CL loaders
-          const uint32_t dst = base + s * kStageBytes + crank * (kAtomBytes / CL);
           const int r0 = row0 + static_cast<int>(crank) * (kNB / CL);
+          if constexpr (PAIR) {
+            // the leader's barrier collects the bytes of both halves; each CTA fills its own ring
+            const uint32_t lbar = mapa_shared(full_bar(s), 0);
+            if (crank == 0) mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(atoms) * kAtomBytes * 2);
+            const uint32_t dst = base + s * kStageBytes;
 #pragma unroll
-          for (int at = 0; at < kAtomsPerStage; ++at) {
-            if (at < atoms) {
-              if constexpr (CL == 1) tma_load_2d(dst + at * kAtomBytes, &tmap, full_bar(s), k0 + at * kAtomK, r0);
-              else tma_load_2d_mc(dst + at * kAtomBytes, &tmap, full_bar(s), k0 + at * kAtomK, r0, kMcMask);
+            for (int at = 0; at < kAtomsPerStage; ++at)
+              if (at < atoms) tma_load_2d_pair(dst + at * kAtomBytes, &tmap, lbar, k0 + at * kAtomK, r0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), static_cast<uint32_t>(atoms) * kAtomBytes);   // bytes from all CL loaders
+            const uint32_t dst = base + s * kStageBytes + crank * (kAtomBytes / CL);
+#pragma unroll
+            for (int at = 0; at < kAtomsPerStage; ++at) {
+              if (at < atoms) {
+                if constexpr (CL == 1) tma_load_2d(dst + at * kAtomBytes, &tmap, full_bar(s), k0 + at * kAtomK, r0);
+                else tma_load_2d_mc(dst + at * kAtomBytes, &tmap, full_bar(s), k0 + at * kAtomK, r0, kMcMask);
+              }
             }
           }
         }
@@ -510,17 +597,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       }
     }
   } else {
-    // ================= MMA issuer (warp 1) =================
-    asm volatile("bar.sync 1, 160;" ::: "memory");   // wait for the A operand
+    // ================= MMA issuer (warp 1; in PAIR mode only the leader CTA's) =================
+    if constexpr (PAIR) {
+      if (crank == 0) mbar_wait(aready_bar, 0);      // 8 epilogue warps of the pair have stored their queries
+    } else {
+      asm volatile("bar.sync 1, 160;" ::: "memory");   // wait for the A operand
+    }
     tc_fence_after();
     uint32_t s = 0, ph = 0, it = 0;
     const uint64_t desc0 = make_b_desc(base);        // descriptor of stage 0, atom 0, k = 0
-    TileWalker walk(a, cj, n_tiles);
+    constexpr uint32_t idesc = PAIR ? kIdescPair : kIdesc;
+    auto mma = [](uint32_t d, uint32_t at, uint64_t bd, uint32_t acc) {
+      if constexpr (PAIR) umma_ts_pair(d, at, bd, idesc, acc);
+      else umma_ts(d, at, bd, idesc, acc);
+    };
+    TileWalker walk(a, cj, (PAIR && crank != 0) ? 0 : n_tiles);     // the peer's MMA warp issues nothing
     int64_t t;
     uint32_t w0, w1;
     while (walk.next(t, w0, w1)) {
-      const int buf = it & 1;
-      const uint32_t par = (it >> 1) & 1;
+      const int buf = it & (nbuf - 1);
+      const uint32_t par = (it >> nbuf_log2) & 1;
       ++it;
       mbar_wait(acce_bar(buf), par ^ 1u);           // epilogue has drained this accumulator buffer
       tc_fence_after();
@@ -543,27 +639,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
               const int g = g0 + j;
               const uint64_t bdesc = dstage + static_cast<uint64_t>(((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4);
               if (g < a.split_steps) {
-                umma_ts(d_tmem, tmem_base + static_cast<uint32_t>(g * 8), bdesc, kIdesc, g > 0 ? 1u : 0u);
-                umma_ts(d_tmem, tmem_base + static_cast<uint32_t>((g + a.split_steps) * 8), bdesc, kIdesc, 1u);
+                mma(d_tmem, tmem_base + static_cast<uint32_t>(g * 8), bdesc, g > 0 ? 1u : 0u);
+                mma(d_tmem, tmem_base + static_cast<uint32_t>((g + a.split_steps) * 8), bdesc, 1u);
               } else {
-                umma_ts(d_tmem, tmem_base + static_cast<uint32_t>((g - a.split_steps) * 8), bdesc, kIdesc, 1u);
+                mma(d_tmem, tmem_base + static_cast<uint32_t>((g - a.split_steps) * 8), bdesc, 1u);
               }
             }
           } else if (left >= kMmasPerStage) {
 #pragma unroll
             for (int j = 0; j < kMmasPerStage; ++j)
-              umma_ts(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4), kIdesc,
-                      (j > 0) ? 1u : (ks > 0 ? 1u : 0u));
+              mma(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4),
+                  (j > 0) ? 1u : (ks > 0 ? 1u : 0u));
           } else {
 #pragma unroll
             for (int j = 0; j < kMmasPerStage; ++j)
               if (j < left)
-                umma_ts(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4), kIdesc,
-                        (j > 0) ? 1u : (ks > 0 ? 1u : 0u));
+                mma(d_tmem, a0 + j * 8, dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4),
+                    (j > 0) ? 1u : (ks > 0 ? 1u : 0u));
           }
-          if constexpr (CL == 1) umma_commit(empty_bar(s));   // stage reusable once these MMAs retire
-          else umma_commit_mc(empty_bar(s), kMcMask);          // ... in every CTA that loads into it
-          if (ks == n_stages_per_tile - 1) umma_commit(accf_bar(buf));
+          if constexpr (PAIR) {
+            umma_commit_pair(empty_bar(s), kMcMask);           // both CTAs' producers may refill their half
+            if (ks == n_stages_per_tile - 1) umma_commit_pair(accf_bar(buf), kMcMask);   // both epilogues may drain
+          } else {
+            if constexpr (CL == 1) umma_commit(empty_bar(s));   // stage reusable once these MMAs retire
+            else umma_commit_mc(empty_bar(s), kMcMask);          // ... in every CTA that loads into it
+            if (ks == n_stages_per_tile - 1) umma_commit(accf_bar(buf));
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
@@ -576,7 +677,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   if constexpr (CL > 1) cluster_sync_all();   // no peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -601,7 +703,7 @@ EncodeTiledFn get_encode() {
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
-  int n_mtiles, cpm, cl;
+  int n_mtiles, cpm, cl, mode;
   size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_merged, total;
 };
 
@@ -611,6 +713,9 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.n_mtiles = (B + kM - 1) / kM;
   L.cl = (L.n_mtiles >= 2) ? 2 : 1;
   if (const char* e = getenv("RAG_B200_TENSOR_CL")) { if (atoi(e) == 1) L.cl = 1; }
+  // two query tiles or more: CTA pairs (cta_group::2); RAG_B200_TENSOR_MODE=1 selects the older multicast pair
+  L.mode = (L.cl == 1) ? 0 : 2;
+  if (const char* e = getenv("RAG_B200_TENSOR_MODE")) { if (L.cl == 2 && atoi(e) == 1) L.mode = 1; }
   L.n_mtiles = (L.n_mtiles + L.cl - 1) / L.cl * L.cl;   // pad with idle query tiles to whole clusters
   L.cpm = sm_count / L.n_mtiles;
   if (L.cpm < 1) L.cpm = 1;
@@ -624,9 +729,10 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   return L;
 }
 
-template <int KL, bool L2, int CL>
+template <int KL, bool L2, int MODE>
 cudaError_t launch_one(const CUtensorMap& tmap, const Args& a, dim3 grid, cudaStream_t st) {
-  auto kern = gemm_topk_kernel<KL, L2, CL>;
+  constexpr int CL = (MODE == 0) ? 1 : 2;
+  auto kern = gemm_topk_kernel<KL, L2, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
@@ -636,8 +742,8 @@ cudaError_t launch_one(const CUtensorMap& tmap, const Args& a, dim3 grid, cudaSt
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = CL;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
@@ -645,9 +751,10 @@ cudaError_t launch_one(const CUtensorMap& tmap, const Args& a, dim3 grid, cudaSt
 }
 
 template <int KL>
-cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int cl, dim3 grid, cudaStream_t st) {
-  if (cl == 2) return l2 ? launch_one<KL, true, 2>(tmap, a, grid, st) : launch_one<KL, false, 2>(tmap, a, grid, st);
-  return l2 ? launch_one<KL, true, 1>(tmap, a, grid, st) : launch_one<KL, false, 1>(tmap, a, grid, st);
+cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int mode, dim3 grid, cudaStream_t st) {
+  if (mode == 2) return l2 ? launch_one<KL, true, 2>(tmap, a, grid, st) : launch_one<KL, false, 2>(tmap, a, grid, st);
+  if (mode == 1) return l2 ? launch_one<KL, true, 1>(tmap, a, grid, st) : launch_one<KL, false, 1>(tmap, a, grid, st);
+  return l2 ? launch_one<KL, true, 0>(tmap, a, grid, st) : launch_one<KL, false, 0>(tmap, a, grid, st);
 }
 
 }  // namespace
@@ -722,17 +829,19 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   a.live = p.live; a.filter = p.filter; a.filter_words = p.filter_words;
   a.n_rows = p.n_rows; a.row_elems = width; a.B = p.B; a.k = kk; a.cpm = L.cpm; a.partial = part;
   a.split_steps = split ? p.row_elems / 16 : 0;
+  a.nbuf = (((width + 15) / 16) * 8 + 4 * kAccCols <= kTmemCols) ? 4 : 2;
+  if (const char* e = getenv("RAG_B200_TENSOR_NBUF")) { if (atoi(e) == 2) a.nbuf = 2; }
   a.dense = p.dense;
   a.prefetch = 0;
   if (const char* e = getenv("RAG_B200_TENSOR_PF")) a.prefetch = atoi(e);
   // lists of CTAs that never see a tile must still read as empty
   e = cudaMemsetAsync(part, 0xFF, static_cast<size_t>(L.cpm) * p.B * kk * 8, st);
   if (e != cudaSuccess) return e;
-  dim3 grid(L.cpm, L.n_mtiles, 1);
+  dim3 grid(L.cpm * L.cl, L.n_mtiles / L.cl, 1);
   const bool l2 = (p.space == 0);
-  if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.cl, grid, st);
-  else if (kk <= 128) e = launch_kl<128>(tmap, a, l2, L.cl, grid, st);
-  else e = launch_kl<1024>(tmap, a, l2, L.cl, grid, st);
+  if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.mode, grid, st);
+  else if (kk <= 128) e = launch_kl<128>(tmap, a, l2, L.mode, grid, st);
+  else e = launch_kl<1024>(tmap, a, l2, L.mode, grid, st);
   if (e != cudaSuccess) return e;
   out->partial = part;
   out->S = L.cpm;
