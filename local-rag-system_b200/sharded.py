@@ -87,15 +87,20 @@ class ShardedSearcher:
         b = self._buf.get(key)
         if b is None:
             dev = self.device
+            # rows | dists | counts live in ONE device block and one pinned host block: a single D2H per batch
+            nr, nd, nc = B * k * 8, B * k * 4, B * 4
+            out = torch.empty(nr + nd + nc, dtype=torch.uint8, device=dev)
+            h_out = torch.empty(nr + nd + nc, dtype=torch.uint8).pin_memory()
             b = {
                 "local": torch.empty(B * k, dtype=torch.int64, device=dev),
-                "rows": torch.empty((B, k), dtype=torch.int64, device=dev),
-                "dists": torch.empty((B, k), dtype=torch.float32, device=dev),
-                "counts": torch.empty(B, dtype=torch.int32, device=dev),
+                "out": out, "h_out": h_out,
+                "rows": out[:nr].view(torch.int64).view(B, k),
+                "dists": out[nr:nr + nd].view(torch.float32).view(B, k),
+                "counts": out[nr + nd:].view(torch.int32),
                 "q": torch.empty((B, self.store.dim), dtype=torch.float32, device=dev),
-                "h_rows": torch.empty((B, k), dtype=torch.int64).pin_memory(),
-                "h_dists": torch.empty((B, k), dtype=torch.float32).pin_memory(),
-                "h_counts": torch.empty(B, dtype=torch.int32).pin_memory(),
+                "h_rows": h_out[:nr].view(torch.int64).view(B, k),
+                "h_dists": h_out[nr:nr + nd].view(torch.float32).view(B, k),
+                "h_counts": h_out[nr + nd:].view(torch.int32),
             }
             self._buf[key] = b
         return b
@@ -136,8 +141,6 @@ class ShardedSearcher:
         b = self._buffers(B, k)
         b["q"].copy_(q if q.is_pinned() else q.pin_memory(), non_blocking=True)
         rows, dists, counts = self.search_device(b["q"], k, mask_slot, regime)
-        b["h_rows"].copy_(rows, non_blocking=True)
-        b["h_dists"].copy_(dists, non_blocking=True)
-        b["h_counts"].copy_(counts, non_blocking=True)
+        b["h_out"].copy_(b["out"], non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return b["h_rows"].numpy().copy(), b["h_dists"].numpy().copy(), b["h_counts"].numpy().copy()
