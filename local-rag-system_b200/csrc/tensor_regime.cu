@@ -266,6 +266,11 @@ struct Args {
   int nbuf;                      // accumulator buffers in tensor memory (2 or 4)
   int split_steps;               // > 0: split-precision rows [hi | lo], the first split_steps k-steps are hi
   uint64_t* partial;             // [cpm][B][k]
+  // [n_mtiles*128] ordered(fp32): smallest k-th-best distance any CTA has reached for this query so far.
+  // The cpm CTAs that share a query each see 1/cpm of the corpus; a row beyond ANY CTA's k-th best cannot
+  // be in the global top-k, so publishing the bound lets every CTA reject with the tightest one
+  // (an order of magnitude fewer list insertions at k = 100).  0xFFFFFFFF = nothing published yet.
+  uint32_t* tau_shared;
 };
 
 // per-thread running top-k.  KL <= 16: sorted list, fully unrolled (registers / L1-resident);
@@ -469,8 +474,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     TopList<KL> top;
     top.init();
     const int k = a.k;
-    float tau = __int_as_float(0x7f800000);          // +inf until the list is full
+    float tau = __int_as_float(0x7f800000);          // rejection threshold: min(own k-th best, shared bound); +inf at first
+    float tau_g = __int_as_float(0x7f800000);        // last shared bound seen
     uint64_t kth_key = kEmptyKey;
+    uint32_t* tau_slot = a.tau_shared + (mt * kM + m);
     const float qn = (L2 && q_valid) ? a.q_norm2[b] : 0.0f;
 
     uint32_t it = 0;
@@ -487,8 +494,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         xn0 = (r0 < a.n_rows) ? __ldg(a.x_norm2 + r0) : 0.0f;
         xn1 = (r1 < a.n_rows) ? __ldg(a.x_norm2 + r1) : 0.0f;
       }
+      // every 8th tile: pick up the bound the sibling CTAs have published (the load overlaps the wait below)
+      const bool refresh = q_valid && ((it & 7u) == 1u);
+      uint32_t tg_bits = 0xFFFFFFFFu;
+      if (refresh) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tg_bits) : "l"(tau_slot) : "memory");
       mbar_wait(accf_bar(buf), par);
       tc_fence_after();
+      if (tg_bits != 0xFFFFFFFFu) {
+        tau_g = fminf(tau_g, ordered_to_float(tg_bits));
+        tau = fminf(tau, tau_g);
+      }
       // both halves of the 64-column accumulator are requested back to back, then the buffer is
       // handed back to the MMA warp before any score is looked at
       uint32_t vv[2][32];
@@ -572,10 +587,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           if (L2) dj = fmaxf(dj, 0.0f);
           else dj = 1.0f - dj;
           const uint64_t key = make_key(dj, static_cast<uint32_t>(t * kNB + half * 32 + j));
-          if (key < kth_key) {
+          if (key < kth_key && dj <= tau_g) {
             top.insert(key, k);
             kth_key = top.kth(k);
-            tau = (kth_key == kEmptyKey) ? __int_as_float(0x7f800000) : key_dist(kth_key);
+            if (kth_key != kEmptyKey) {              // list is full: its k-th best bounds the global k-th best
+              const float own = key_dist(kth_key);
+              atomicMin(tau_slot, float_to_ordered(own));
+              tau = fminf(own, tau_g);
+            }
           }
         }
       }
@@ -677,17 +696,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           if (a.split_steps > 0) {
             // fp32 store contracted as bf16 pairs: q.x ~ qh.xh + ql.xh + qh.xl  (ql.xl < 2^-18 |q||x| dropped).
             // B k-step g of the [hi | lo] shadow row pairs with A columns of q_hi (and q_lo while g is a hi step).
+            // fully unrolled so that the descriptor offsets are immediates and everything stays in uniform
+            // registers (a rolled loop issued one MMA per ~100 cycles: 3.0 ms instead of ~1.5 for 1M x 384)
             const int g0 = ks * kMmasPerStage;
-            const int nst = left < kMmasPerStage ? left : kMmasPerStage;
-#pragma unroll 1
-            for (int j = 0; j < nst; ++j) {
-              const int g = g0 + j;
-              const uint64_t bdesc = dstage + static_cast<uint64_t>(((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4);
-              if (g < a.split_steps) {
-                mma(d_tmem, tmem_base + static_cast<uint32_t>(g * 8), bdesc, g > 0 ? 1u : 0u);
-                mma(d_tmem, tmem_base + static_cast<uint32_t>((g + a.split_steps) * 8), bdesc, 1u);
-              } else {
-                mma(d_tmem, tmem_base + static_cast<uint32_t>((g - a.split_steps) * 8), bdesc, 1u);
+            const int sp = a.split_steps;
+            const uint32_t a_hi = tmem_base + static_cast<uint32_t>(g0 * 8);          // q_hi columns of this stage's first k-step
+            const uint32_t a_lo = a_hi + static_cast<uint32_t>(sp * 8);              // matching q_lo columns
+            const uint32_t a_hx = a_hi - static_cast<uint32_t>(sp * 8);              // q_hi columns for an x_lo k-step
+#pragma unroll
+            for (int j = 0; j < kMmasPerStage; ++j) {
+              if (j < left) {
+                const uint64_t bdesc = dstage + (((j >> 2) * kAtomBytes + (j & 3) * 32) >> 4);
+                if (g0 + j < sp) {
+                  mma(d_tmem, a_hi + j * 8, bdesc, (g0 + j > 0) ? 1u : 0u);
+                  mma(d_tmem, a_lo + j * 8, bdesc, 1u);
+                } else {
+                  mma(d_tmem, a_hx + j * 8, bdesc, 1u);
+                }
               }
             }
           } else if (left >= kMmasPerStage) {
@@ -749,7 +774,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
   int n_mtiles, cpm, cl, mode;
-  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_merged, total;
+  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_tau, off_merged, total;
 };
 
 // row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
@@ -769,6 +794,7 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.off_qnorm = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);
   L.off_qf32 = off;  off += align256(static_cast<size_t>(B) * row_elems * 4);
   L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
+  L.off_tau = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);      // directly behind `partial`: one memset
   L.off_merged = off; off += align256(static_cast<size_t>(B) * k * 8);
   L.total = off;
   return L;
@@ -880,7 +906,8 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   a.prefetch = 0;
   if (const char* e = getenv("RAG_B200_TENSOR_PF")) a.prefetch = atoi(e);
   // lists of CTAs that never see a tile must still read as empty
-  e = cudaMemsetAsync(part, 0xFF, static_cast<size_t>(L.cpm) * p.B * kk * 8, st);
+  a.tau_shared = reinterpret_cast<uint32_t*>(p.scratch + L.off_tau);
+  e = cudaMemsetAsync(part, 0xFF, (L.off_tau - L.off_partial) + static_cast<size_t>(L.n_mtiles) * kM * 4, st);
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm * L.cl, L.n_mtiles / L.cl, 1);
   const bool l2 = (p.space == 0);

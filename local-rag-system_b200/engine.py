@@ -186,15 +186,26 @@ class Exchange:
     def __init__(self, device: int, rank: int, world: int, all_gather_bytes, slot_keys: int = 8192):
         self._lib = N.load()
         h = C.c_void_p()
-        N.check(self._lib.rag_exchange_create(int(device), int(rank), int(world), int(slot_keys), C.byref(h)))
-        self._h = h
+        self._h = None
         self.rank, self.world, self.slot_keys = rank, world, slot_keys
         mine = C.create_string_buffer(N.EXCHANGE_HANDLE_BYTES)
-        N.check(self._lib.rag_exchange_handle(self._h, mine))
+        rc = self._lib.rag_exchange_create(int(device), int(rank), int(world), int(slot_keys), C.byref(h))
+        msg = N.last_error() if rc != 0 else ""
+        if rc == 0:
+            self._h = h
+            rc = self._lib.rag_exchange_handle(self._h, mine)
+            msg = N.last_error() if rc != 0 else ""
+        # the all-gather is collective: take part even if creating / exporting the buffer failed, then report
         everyone = bytes(all_gather_bytes(mine.raw))
-        if len(everyone) != world * N.EXCHANGE_HANDLE_BYTES:
-            raise ValueError("all_gather_bytes must return world x 64 bytes")
-        N.check(self._lib.rag_exchange_connect(self._h, everyone))
+        try:
+            if rc != 0:
+                raise N.EngineError(f"[rag_b200 {rc}] {msg}")
+            if len(everyone) != world * N.EXCHANGE_HANDLE_BYTES:
+                raise ValueError("all_gather_bytes must return world x 64 bytes")
+            N.check(self._lib.rag_exchange_connect(self._h, everyone))
+        except Exception:
+            self.close()
+            raise
 
     @property
     def handle(self):

@@ -66,7 +66,28 @@ class ShardedSearcher:
         self.exchange: Optional[Exchange] = None
         self.last_path = None
         if world > 1 and fused_exchange and os.environ.get("RAG_B200_FUSED_EXCHANGE", "1") != "0":
-            self.exchange = Exchange(store.device, rank, world, self._all_gather_bytes)
+            self.exchange = self._connect_exchange()
+
+    def _connect_exchange(self) -> Optional[Exchange]:
+        """Map every rank's exchange buffer (CUDA IPC).  Collective: if mapping fails on ANY rank (no peer
+        access, IPC not permitted in the container) every rank drops to the NCCL exchange -- a mixed setup
+        would deadlock."""
+        x, err = None, None
+        try:
+            x = Exchange(self.store.device, self.rank, self.world, self._all_gather_bytes)
+        except Exception as e:       # noqa: BLE001 - reported below, the NCCL path still works
+            err = e
+        ok = torch.tensor([0 if x is None else 1], device=self.device, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            return x
+        if x is not None:
+            x.close()
+        if self.rank == 0:
+            import warnings
+            warnings.warn(f"fused cross-GPU exchange unavailable ({err or 'a peer could not map the buffers'}); "
+                          "using the NCCL all-gather + merge kernel instead")
+        return None
 
     def _all_gather_bytes(self, mine: bytes) -> bytes:
         t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.device)

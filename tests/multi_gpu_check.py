@@ -95,12 +95,20 @@ def fp32_and_empty_shard_cases(rank, world, local):
         fused = ShardedSearcher(shard, rank, world, row_base=lo, fused_exchange=True)
         q = unit_rows(B, dim, 22)
         for rep in range(3):                              # epochs 1..3: both buffer halves get reused
-            want = full.query(q, k)
-            got = fused.search(q, k)
+            want = full.query(q, k, regime="stream")
+            got = fused.search(q, k, regime="stream")
             good = all(np.array_equal(g, w) for g, w in zip(got, want)) and fused.last_path == "fused"
             if not good:
                 print(f"[rank {rank}] MISMATCH fp32/empty-shard case n={n} rep={rep} path={fused.last_path}", flush=True)
             ok = ok and good
+        # automatic regime (B = 20 on an fp32 store -> split-precision tensor regime + NCCL exchange): same answer
+        want = full.query(q, k)
+        got = fused.search(q, k)
+        good = np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2]) and \
+            np.allclose(got[1], want[1], rtol=1e-5, atol=2e-6)
+        if not good:
+            print(f"[rank {rank}] MISMATCH fp32 auto-regime case n={n} path={fused.last_path}", flush=True)
+        ok = ok and good
         ok = ok and not fused.exchange.timed_out()
         fused.close()
         shard.close()

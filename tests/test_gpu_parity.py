@@ -141,6 +141,47 @@ def test_tombstones_masks_and_row_reuse():
         st.close()
 
 
+@pytest.mark.parametrize("dtype,dim,B", [("bf16", 384, 1), ("bf16", 192, 2), ("bf16", 768, 1), ("f32", 192, 3),
+                                         ("f32", 96, 1), ("bf16", 100, 2)])
+def test_filtered_walk_all_row_layouts(dtype, dim, B):
+    """`where` bitmaps drive the gathered walk (256-row chunks, n-th-set-bit row selection); cover the
+    sub-warp row layouts (16 / 8 lanes per row), the generic layout, ragged ends, chunk-dense and
+    chunk-sparse patterns and the switch between gathered and blocked order."""
+    n, k = 20_011, 10
+    x = unit_rows(n, dim, 61)
+    q = unit_rows(B, dim, 62)
+    if dtype == "bf16":
+        x, q = round_to_bf16(x), round_to_bf16(q)
+    rng = np.random.default_rng(63)
+    st = DeviceStore(dim, dtype, "cosine")
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        live = np.ones(n, bool)
+        dead = rng.choice(n, 700, replace=False)
+        st.delete(dead)
+        live[dead] = False
+        patterns = {
+            "1%": rng.random(n) < 0.01, "10%": rng.random(n) < 0.1, "30%": rng.random(n) < 0.3, "70%": rng.random(n) < 0.7,
+            "every 256th": (np.arange(n) % 256) == 255,
+            "one chunk": (np.arange(n) // 256) == 17,
+            "one word": (np.arange(n) // 32) == 201,
+            "last rows": np.arange(n) >= n - 5,
+            "first row": np.arange(n) == 0,
+            "mixed": ((np.arange(n) // 256) % 3 == 0) | (rng.random(n) < 0.02),     # dense chunks next to sparse ones
+        }
+        for name, passing in patterns.items():
+            st.set_mask(2, passing)
+            rows, dists, counts = st.query(q, k, mask_slot=2, regime="stream")
+            try:
+                check_against_oracle("cosine", dtype, stored, q, k, rows, dists, counts, valid=live & passing,
+                                     min_recall=1.0 if dtype == "f32" else 0.999)
+            except AssertionError as e:
+                raise AssertionError(f"pattern {name!r}: {e}") from e
+    finally:
+        st.close()
+
+
 def test_edge_cases():
     st = DeviceStore(8, "f32", "l2")
     try:

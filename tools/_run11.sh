@@ -1,0 +1,9 @@
+set -u
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29511 tests/multi_gpu_check.py > gpurun_out/multi_gpu_check8.log 2>&1; echo "check rc=$?"; grep -v "^W\|^\*\|OMP_NUM" gpurun_out/multi_gpu_check8.log | tail -8
+sum() { tail -1 $1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read()); print(d['n_gpus'],'gpus | QPS %.0f ms %.4f p50 %.4f e2e %.0f (p50 %.4f) | launches %d | %s'%(d['value'],d['ms_per_step'],d['p50_ms'],d['e2e']['value'],d['e2e']['p50_ms'],d['gpu_launches'],d['config']['sharding'][:60])); print('   regimes', [(r['batch'], round(r['value']), round(r['roofline']['frac'],2)) for r in d.get('regimes',[])], d['clocks'])"; }
+timeout 600 $TR --master-port 29512 bench.py --gpus 8 --steps 1000 --warmup 20 > gpurun_out/bench_8gpu_b1.log 2>&1; echo "bench rc=$?"; sum gpurun_out/bench_8gpu_b1.log
+RAG_B200_FUSED_EXCHANGE=0 timeout 600 $TR --master-port 29513 bench.py --gpus 8 --steps 1000 --warmup 20 --extra-batches "" > gpurun_out/bench_8gpu_b1_nccl.log 2>&1; echo "bench rc=$?"; sum gpurun_out/bench_8gpu_b1_nccl.log
+timeout 600 $TR --master-port 29514 bench.py --gpus 8 --batch 1024 --steps 50 --warmup 5 --extra-batches "" > gpurun_out/bench_8gpu_b1024.log 2>&1; echo "bench rc=$?"; sum gpurun_out/bench_8gpu_b1024.log
