@@ -155,6 +155,12 @@ class ShardedSearcher:
     def search(self, queries: np.ndarray, k: int, mask_slot: int = -1, regime: str = "auto"):
         """Host-to-host call: pinned H2D of the queries, shard search, exchange,
         merge, D2H of the final B x k result.  Returns numpy (rows, dists, counts)."""
+        if self.world == 1:
+            # one shard: the engine's own host-buffer call (pinned staging, H2D, search, one D2H, sync -- all in C)
+            rows, dists, counts = self.store.query(queries, k, mask_slot=mask_slot, regime=regime)
+            if self.row_base:
+                rows = np.where(rows >= 0, rows + self.row_base, rows)
+            return rows, dists, counts
         q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
         if q.ndim == 1:
             q = q[None, :]

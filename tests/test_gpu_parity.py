@@ -514,3 +514,58 @@ def test_tensor_regime_large_properties():
         assert np.array_equal(r3[:, :k - 1], rows[:, 1:])
     finally:
         st.close()
+
+
+def test_headline_size_10m_768_properties():
+    """BASELINE.json's headline shape (10M x 768 bf16, cosine, top-10) through size-independent
+    properties; the corpus is generated on the device (torch is only the random-number source)."""
+    import torch
+    n, dim, k = 10_000_000, 768, 10
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(2024)
+    st = DeviceStore(dim, "bf16", "cosine", capacity_hint=n)
+    try:
+        chunk = 500_000
+        for s0 in range(0, n, chunk):
+            xs = torch.randn((chunk, dim), generator=gen, device=dev, dtype=torch.float32)
+            torch.cuda.synchronize(dev)
+            st.upsert_device(xs.data_ptr(), chunk)
+            del xs
+        assert st.count() == n
+        planted = np.array([17, 123_456, 4_999_999, 5_000_000, 9_999_999, 7_654_321, 31, 2_500_000])
+        stored = st.fetch(planted)                                  # the normalised, bf16-rounded rows
+        rng = np.random.default_rng(5)
+        q = stored + 0.02 * rng.standard_normal(stored.shape).astype(np.float32)
+        q = round_to_bf16(q / np.linalg.norm(q, axis=1, keepdims=True))
+        rows1 = []
+        for b in range(len(planted)):                               # B = 1: the stream regime, one launch per query
+            r, d, c = st.query(q[b], k)
+            assert st.last_query_info()["regime"] == "stream" and c[0] == k
+            assert np.all(np.diff(d[0]) >= 0)
+            rows1.append(r[0])
+            want = 1.0 - float(q[b].astype(np.float64) @ stored[b].astype(np.float64))
+            assert r[0, 0] == planted[b] and abs(d[0, 0] - want) < 2e-6
+        rows1 = np.stack(rows1)
+        qq = np.vstack([q, round_to_bf16(unit_rows(56, dim, 6))])    # B = 64: the tensor regime
+        rt, dt, ct = st.query(qq, k)
+        assert st.last_query_info()["regime"] == "tensor" and np.all(ct == k)
+        assert np.array_equal(rt[:len(planted)], rows1)             # both regimes pick the same rows
+        rs, ds, _ = st.query(qq[8:16], k, regime="stream")
+        assert np.array_equal(rs, rt[8:16]) and np.allclose(ds, dt[8:16], rtol=1e-5, atol=2e-6)
+        # top-k(all) == merge(top-k(even rows), top-k(odd rows)), through the `where` bitmap path
+        even = (np.arange(n) % 2) == 0
+        st.set_mask(0, even)
+        st.set_mask(1, ~even)
+        r0, d0, _ = st.query(q[:2], k, mask_slot=0)
+        r1, d1, _ = st.query(q[:2], k, mask_slot=1)
+        for b in range(2):
+            allr, alld = np.concatenate([r0[b], r1[b]]), np.concatenate([d0[b], d1[b]])
+            o = np.lexsort((allr, alld))[:k]
+            assert allr[o].tolist() == rows1[b].tolist()
+        # deleting the winners promotes the runners-up
+        st.delete(rows1[:, 0])
+        r2, _, _ = st.query(qq, k)
+        assert np.array_equal(r2[:len(planted), :k - 1], rt[:len(planted), 1:])
+    finally:
+        st.close()
