@@ -271,7 +271,14 @@ struct Args {
   // be in the global top-k, so publishing the bound lets every CTA reject with the tightest one
   // (an order of magnitude fewer list insertions at k = 100).  0xFFFFFFFF = nothing published yet.
   uint32_t* tau_shared;
+  // [cpm][gridDim.y] inverted tile counters (0xFFFFFFFF - tiles issued) of the clusters that walk the same
+  // corpus tiles for different query tiles.  A cluster may run at most kPaceWindow tiles ahead of its slowest
+  // sibling, so a tile fetched from DRAM by the first cluster is still in L2 when the others ask for it
+  // (without pacing the siblings drift apart and every tile is read from DRAM about twice).
+  uint32_t* progress;
+  uint32_t pace_window;          // tiles a cluster may run ahead of its slowest sibling
 };
+constexpr size_t kPaceBytes = 56u << 20;  // L2 budget (of 126 MB) for the tiles between the slowest and the fastest sibling
 
 // per-thread running top-k.  KL <= 16: sorted list, fully unrolled (registers / L1-resident);
 // larger k: a binary MAX-heap in local memory (root = current k-th best): an insertion is a
@@ -617,7 +624,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     TileWalker walk(a, cj, n_tiles);
     int64_t t;
     uint32_t w0, w1;
+    const int n_sib = (a.progress != nullptr) ? static_cast<int>(gridDim.y) : 1;   // clusters sharing this cj's tiles
+    uint32_t* prog = a.progress + static_cast<size_t>(cj) * n_sib;
+    uint32_t ti = 0;                                           // tiles this CTA has issued
     while (walk.next(t, w0, w1)) {
+      if (n_sib > 1 && (ti & 3u) == 0u) {
+        if (crank == 0 && lane == 0)
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog + blockIdx.y), "r"(0xFFFFFFFFu - ti) : "memory");
+        if (ti >= a.pace_window) {
+          for (int spins = 0; spins < 100000; ++spins) {       // bounded: pacing is an optimisation, never a dependency
+            uint32_t v = 0u;
+            if (lane < n_sib) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(prog + lane) : "memory");
+            const uint32_t slowest = __reduce_min_sync(0xffffffffu, 0xFFFFFFFFu - v);
+            if (slowest + a.pace_window >= ti) break;
+            __nanosleep(200);
+          }
+        }
+      }
+      ++ti;
       const int row0 = static_cast<int>(t * kNB);
       // pull this CTA's slice of a tile kPrefetchTiles steps ahead into L2 (hides DRAM latency
       // when the CTAs sharing a corpus tile have drifted apart and it is no longer L2-resident)
@@ -660,6 +684,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
+    if (n_sib > 1 && crank == 0 && lane == 0)                 // finished: nobody should ever wait for this cluster
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog + blockIdx.y), "r"(0u) : "memory");
   } else {
     // ================= MMA issuer (warp 1; in PAIR mode only the leader CTA's) =================
     if constexpr (PAIR) {
@@ -774,7 +800,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
   int n_mtiles, cpm, cl, mode;
-  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_tau, off_merged, total;
+  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_tau, off_prog, off_merged, total;
 };
 
 // row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
@@ -795,6 +821,7 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.off_qf32 = off;  off += align256(static_cast<size_t>(B) * row_elems * 4);
   L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
   L.off_tau = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);      // directly behind `partial`: one memset
+  L.off_prog = off; off += align256(static_cast<size_t>(L.cpm) * L.n_mtiles * 4);  // ... which also covers the pacing counters
   L.off_merged = off; off += align256(static_cast<size_t>(B) * k * 8);
   L.total = off;
   return L;
@@ -907,7 +934,23 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   if (const char* e = getenv("RAG_B200_TENSOR_PF")) a.prefetch = atoi(e);
   // lists of CTAs that never see a tile must still read as empty
   a.tau_shared = reinterpret_cast<uint32_t*>(p.scratch + L.off_tau);
-  e = cudaMemsetAsync(part, 0xFF, (L.off_tau - L.off_partial) + static_cast<size_t>(L.n_mtiles) * kM * 4, st);
+  a.progress = reinterpret_cast<uint32_t*>(p.scratch + L.off_prog);
+  {
+    const size_t tile_bytes = static_cast<size_t>(kNB) * width * 2;
+    size_t w = kPaceBytes / (static_cast<size_t>(L.cpm) * tile_bytes);
+    a.pace_window = static_cast<uint32_t>(w < 8 ? 8 : (w > 4096 ? 4096 : w));
+  }
+  // Off unless RAG_B200_TENSOR_PACE=<window in tiles, or 1 for the default window> is set.  Measured on B200
+  // (10M x 768, B = 1024): pacing cuts the kernel's DRAM reads from 30.5 GB to 18.0 GB (corpus 15.4 GB) but
+  // not its time (12.9 -> 13.0-13.2 ms: the re-reads run at a third of the HBM rate and are not the bound),
+  // and at D = 384 the coupling of the sibling clusters costs 20-30 %.  Kept as an experiment switch.
+  {
+    const char* e = getenv("RAG_B200_TENSOR_PACE");
+    const int v = e ? atoi(e) : 0;
+    if (v <= 0) a.progress = nullptr;
+    else if (v > 1) a.pace_window = static_cast<uint32_t>(v);
+  }
+  e = cudaMemsetAsync(part, 0xFF, (L.off_prog - L.off_partial) + static_cast<size_t>(L.cpm) * L.n_mtiles * 4, st);
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm * L.cl, L.n_mtiles / L.cl, 1);
   const bool l2 = (p.space == 0);

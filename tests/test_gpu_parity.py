@@ -326,8 +326,9 @@ def test_tensor_regime_matches_oracle(space, n, dim, B, k):
         st.close()
 
 
-def test_tensor_regime_masks_tombstones_and_tile_skipping():
-    n, dim, k, B = 6000, 384, 10, 33
+@pytest.mark.parametrize("B", [33, 200])       # one query tile (single CTAs) / two (cta_group::2 pairs)
+def test_tensor_regime_masks_tombstones_and_tile_skipping(B):
+    n, dim, k = 6000, 384, 10
     x = round_to_bf16(unit_rows(n, dim, 21))
     q = round_to_bf16(unit_rows(B, dim, 22))
     rng = np.random.default_rng(23)
