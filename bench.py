@@ -341,6 +341,8 @@ def main():
     e2e_value = B * K / (float(t.item()) / 1e3)
     lat.sort()
     clocks = sampler.stop() if sampler else None
+    if searcher.exchange is not None and searcher.exchange.timed_out():
+        raise SystemExit(f"[rank {rank}] the fused exchange timed out waiting for a peer: results are invalid")
 
     # ---- roofline of the dominant kernel (scan), CUDA events on its own stream ----
     kms = []

@@ -175,7 +175,7 @@ RAG_API int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* 
  *   rag_exchange_connect  maps every peer's buffer
  * All ranks must then issue the same sequence of rag_store_query_fused_dev calls
  * (same B, k), each on one stream per exchange; results (GLOBAL rows) land on every
- * rank.  A rank whose peers never show up gives up after 4 s and sets the status
+ * rank.  A rank whose peers never show up gives up after 20 s and sets the status
  * word (rag_exchange_status) instead of hanging the GPU.
  * rag_store_fused_ok() tells whether a (B, k, flags) batch is served by this path
  * (stream regime, k <= 128, B * k <= slot_keys); otherwise use rag_store_query_dev +

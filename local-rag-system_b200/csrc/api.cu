@@ -388,7 +388,7 @@ size_t search_scratch_bytes(const rag_store* s, int B, int k, int grid_x) {
 
 int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
                   int mask_slot, int regime, uint32_t row_base, const SearchOut& out, bool timed,
-                  rag_exchange* xchg = nullptr) {
+                  rag_exchange* xchg = nullptr, bool forced_tensor = false) {
   cudaStream_t st = c->stream;
   const int grid_x = scan_stream_grid_x(s->sm_count, s->rows);
   float* d_q = reinterpret_cast<float*>(scratch);
@@ -408,13 +408,16 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   int launches = 0;
   int S = 0;
   tensor::Result tres{};
+  if (regime == 2 && s->dtype == RAG_DTYPE_F32) {
+    // the split-precision regime needs the hi/lo shadow (as many bytes again as the rows).  If the device
+    // cannot hold it, an AUTO query is still answered -- exactly, by the stream kernel, just slower.
+    const int rcs = ensure_shadow(s, st);
+    if (rcs == RAG_ENOMEM && !forced_tensor) regime = 1;
+    else if (rcs != RAG_OK) return rcs;
+  }
   if (regime == 2) {
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     tensor::Problem p{};
-    if (s->dtype == RAG_DTYPE_F32) {
-      int rcs = ensure_shadow(s, st);
-      if (rcs != RAG_OK) return rcs;
-    }
     p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.norms2 = s->d_norms2; p.n_rows = s->rows; p.row_elems = s->row_elems;
     p.dim = s->dim; p.dtype = s->dtype; p.space = s->space;
     p.live = s->d_live; p.filter = filter; p.filter_words = fwords;
@@ -827,8 +830,9 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
 
     memcpy(c->h_pin, queries + (size_t)b0 * s->dim, (size_t)Bc * s->dim * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(d_in, c->h_pin, (size_t)Bc * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = search_device(s, c, scratch, Bc, d_in, k, mask_slot, regime, 0u, so, true);
+    rc = search_device(s, c, scratch, Bc, d_in, k, mask_slot, regime, 0u, so, true, nullptr, flags == RAG_QUERY_FORCE_TENSOR);
     if (rc != RAG_OK) return rc;
+    regime_used = s->last_regime.load();     // the regime that actually ran (an fp32 store may have fallen back)
     // one D2H for rows + dists + counts (contiguous in the scratch and in the pinned buffer)
     CUDA_TRY(cudaMemcpyAsync(c->h_pin + in_b, d + in_b, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -876,7 +880,7 @@ int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, int k, in
   so.rows = out_rows_dev;
   so.dists = out_dists_dev;
   so.counts = out_counts_dev;
-  return search_device(s, c, c->d_buf, B, queries_dev, k, mask_slot, regime, row_base, so, false);
+  return search_device(s, c, c->d_buf, B, queries_dev, k, mask_slot, regime, row_base, so, false, nullptr, flags == RAG_QUERY_FORCE_TENSOR);
 }
 
 // ---- fused cross-shard exchange (multi-GPU, stream regime) ---------------------------------

@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.xchg_peers[a.xchg_rank]) + flag_idx + threadIdx.x;
       const unsigned long long t0 = global_timer_ns();
       while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - a.xchg_epoch) < 0) {
-        if (global_timer_ns() - t0 > 4000000000ull) {     // 4 s: a peer never launched; flag it, do not hang the GPU
+        if (global_timer_ns() - t0 > 20000000000ull) {    // 20 s: a peer never launched; flag it, do not hang the GPU
           atomicOr(reinterpret_cast<unsigned int*>(a.xchg_peers[a.xchg_rank] + kXchgStatusOff), 1u + threadIdx.x);
           break;
         }

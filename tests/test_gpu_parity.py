@@ -570,3 +570,27 @@ def test_headline_size_10m_768_properties():
         assert np.array_equal(r2[:len(planted), :k - 1], rt[:len(planted), 1:])
     finally:
         st.close()
+
+
+def test_single_shard_searcher_matches_store_query():
+    """ShardedSearcher with one shard (bench.py's N = 1 path): host-buffer search == DeviceStore.query with the
+    shard's row base added; the asynchronous device-buffer call returns the same."""
+    import torch
+    from local_rag_system_b200.sharded import ShardedSearcher
+    n, dim, k = 3000, 128, 7
+    x = unit_rows(n, dim, 71)
+    q = unit_rows(5, dim, 72)
+    st = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        want_r, want_d, want_c = st.query(q, k)
+        s1 = ShardedSearcher(st, 0, 1, row_base=1000)
+        r, d, c = s1.search(q, k)
+        assert np.array_equal(r, want_r + 1000) and np.array_equal(d, want_d) and np.array_equal(c, want_c)
+        rd, dd, cd = s1.search_device(torch.from_numpy(q).cuda(), k)
+        torch.cuda.synchronize()
+        assert np.array_equal(rd.cpu().numpy(), want_r + 1000) and np.array_equal(dd.cpu().numpy(), want_d)
+        assert np.array_equal(cd.cpu().numpy(), want_c)
+        s1.close()
+    finally:
+        st.close()
