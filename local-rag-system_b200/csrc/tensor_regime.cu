@@ -62,7 +62,8 @@ template <int MODE> struct Ring {
 constexpr int kRingBytes = 7 * kAtomsPerStage * kNB * kAtomK * 2;
 constexpr int kPrefetchTiles = 4;                      // L2 prefetch distance, in this CTA's tiles
 constexpr int kMmasPerStage = kStageK / 16;            // 16
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;            // TMA producer, MMA issuer A, 4 epilogue warps, MMA issuer B
+constexpr int kMmaWarpB = 6;
 constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kMaxKCols = 384;       // A operand: up to 768 bf16 per query
@@ -423,8 +424,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     const Args& a;
     int64_t t, n_tiles;
     uint32_t p0, p1;      // prefetched mask words of tile t
+    bool masks;           // false: the caller only needs the tile sequence (dense stores: nothing to compute)
     __device__ __forceinline__ void fetch() {
       if (t >= n_tiles) { p0 = p1 = 0u; return; }
+      if (a.dense && !masks) { p0 = 1u; p1 = 0u; return; }
       if (a.dense) {
         const int64_t left = a.n_rows - t * kNB;
         p0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
@@ -438,7 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         p1 &= (2 * t + 1 < a.filter_words) ? __ldg(a.filter + 2 * t + 1) : 0u;
       }
     }
-    __device__ __forceinline__ TileWalker(const Args& a_, int64_t t0, int64_t n) : a(a_), t(t0), n_tiles(n) { fetch(); }
+    __device__ __forceinline__ TileWalker(const Args& a_, int64_t t0, int64_t n, bool masks_ = true)
+        : a(a_), t(t0), n_tiles(n), masks(masks_) { fetch(); }
     __device__ __forceinline__ bool next(int64_t& tile, uint32_t& w0, uint32_t& w1) {
       while (t < n_tiles) {
         tile = t; w0 = p0; w1 = p1;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     }
   };
 
-  if (warp >= kEpiWarp0) {
+  if (warp >= kEpiWarp0 && warp < kEpiWarp0 + 4) {
     // ================= epilogue warps: load A into TMEM, then drain accumulators =================
     const int lg = warp & 3;                       // TMEM lane group this warp may access
     const int m = lg * 32 + lane;                  // query row inside the tile
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(aready_bar, 0));
     } else {
-      asm volatile("bar.sync 1, 160;" ::: "memory");   // epilogue warps (128) + MMA warp (32): A operand is in TMEM
+      asm volatile("bar.sync 1, 192;" ::: "memory");   // epilogue warps (128) + both MMA warps (64): A operand is in TMEM
     }
 
     TopList<KL> top;
@@ -621,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   } else if (warp == 0) {
     // ================= TMA producer (whole warp walks the loop, one elected lane issues) =========
     uint32_t s = 0, ph = 0;
-    TileWalker walk(a, cj, n_tiles);
+    TileWalker walk(a, cj, n_tiles, false);
     int64_t t;
     uint32_t w0, w1;
     const int n_sib = (a.progress != nullptr) ? static_cast<int>(gridDim.y) : 1;   // clusters sharing this cj's tiles
@@ -687,11 +691,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     if (n_sib > 1 && crank == 0 && lane == 0)                 // finished: nobody should ever wait for this cluster
       asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog + blockIdx.y), "r"(0u) : "memory");
   } else {
-    // ================= MMA issuer (warp 1; in PAIR mode only the leader CTA's) =================
+    // ================= MMA issuers (warps 1 and 6; in PAIR mode only the leader CTA's) =================
+    // TWO issuing warps take alternate tiles.  A tile costs the issuing thread ~310 (D = 384) to ~450
+    // (D = 768) mostly dependent scalar/uniform instructions (barrier polls, descriptor and column
+    // arithmetic, 3 per MMA) at ~4.7 cycles each -- 1.5-2.1 k cycles, MORE than the tile's 768-1536
+    // cycles on the tensor pipe (ncu: the single issuer was never back-pressured by UTCHMMA, it was simply
+    // busy).  The MMAs of consecutive tiles touch different accumulators and ring stages, so two threads
+    // can issue them independently; each commits what it issued.
     if constexpr (PAIR) {
       if (crank == 0) mbar_wait(aready_bar, 0);      // 8 epilogue warps of the pair have stored their queries
     } else {
-      asm volatile("bar.sync 1, 160;" ::: "memory");   // wait for the A operand
+      asm volatile("bar.sync 1, 192;" ::: "memory");   // wait for the A operand
     }
     tc_fence_after();
     uint32_t s = 0, ph = 0, it = 0;
@@ -701,13 +711,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       if constexpr (PAIR) umma_ts_pair(d, at, bd, idesc, acc);
       else umma_ts(d, at, bd, idesc, acc);
     };
-    TileWalker walk(a, cj, (PAIR && crank != 0) ? 0 : n_tiles);     // the peer's MMA warp issues nothing
+    TileWalker walk(a, cj, (PAIR && crank != 0) ? 0 : n_tiles, false);     // the peer's MMA warps issue nothing
+    const uint32_t issuer = (warp == kMmaWarpB) ? 1u : 0u;
+    const uint32_t n_ring = static_cast<uint32_t>(kStages);
     int64_t t;
     uint32_t w0, w1;
     while (walk.next(t, w0, w1)) {
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
+      const bool mine = (it & 1u) == issuer;
       ++it;
+      if (!mine) {                                  // the other issuer's tile: step over its ring stages
+        s += static_cast<uint32_t>(n_stages_per_tile);
+        if (s >= n_ring) { s -= n_ring; ph ^= 1u; }
+        continue;
+      }
       mbar_wait(acce_bar(buf), par ^ 1u);           // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_tmem = tmem_acc + static_cast<uint32_t>(buf * kAccCols);
