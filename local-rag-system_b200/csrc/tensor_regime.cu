@@ -1,32 +1,32 @@
 // K3 + K4: tensor-core search regime for large query batches.
 //
-// Replaces, for B > 8 queries, the hnswlib graph walk / numpy brute force behind
-// collection.query (api/app.py:544-549) with an exact dense contraction
-// Q[B x D] . X[N x D]^T on the 5th-generation tensor cores, with the top-k
-// selection fused into the epilogue so the B x N score matrix never exists.
+// Replaces, for B > 3 queries (B > 8 on fp32 stores), the hnswlib graph walk / numpy brute force
+// behind collection.query (api/app.py:544-549) with an exact dense contraction
+// Q[B x D] . X[N x D]^T on the 5th-generation tensor cores, with the top-k selection fused into
+// the epilogue so the B x N score matrix never exists.
 //
-// Design (sm_100a only; tcgen05 + TMEM + TMA):
-//   * one persistent CTA per SM, dedicated for its whole life to ONE tile of 128
-//     queries (the MMA M dimension).  The 128 x D bf16 query tile is loaded ONCE
-//     into TENSOR MEMORY (D/2 columns) and used as the A operand from TMEM
-//     (tcgen05.mma ... [d_tmem], [a_tmem], b_desc): the queries never touch shared
-//     memory or L2 again, so on-chip traffic is the corpus stream only.
-//   * the corpus streams HBM -> TMA (128B-swizzled boxes of 64 rows x 64 elements)
-//     -> a 7-stage x 32 KB = 224 KB shared-memory ring -> tcgen05.mma as the B operand;
-//     tiles a few steps ahead are pulled into L2 with cp.async.bulk.prefetch.tensor.
-//     Every corpus byte is read from HBM once per batch (CTAs serving different
-//     query tiles walk the corpus tiles in the same order, so re-reads hit L2).
-//   * accumulators: 2 x 64 fp32 columns of TMEM (double buffered): while the
-//     tensor core contracts corpus tile i+1, four epilogue warps drain tile i with
-//     tcgen05.ld (thread = one query, 64 scores), test them against the query's
-//     running k-th best distance and insert the rare survivors into a per-thread
-//     sorted list (registers for k <= 16).  live/filter bitmaps are applied on the
-//     survivor path; tiles whose 64 rows are all dead or filtered are skipped.
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) and
-//     TMEM owner, warps 2-5 = epilogue.
+// Design (sm_100a only; tcgen05 + TMEM + TMA; measurements and the reasons in DESIGN.md 3.2 / 3.3):
+//   * one persistent CTA per SM, dedicated for its whole life to ONE tile of 128 queries (the MMA M
+//     dimension).  The 128 x D bf16 query tile is written ONCE into TENSOR MEMORY (D/2 columns) and
+//     used as the A operand from TMEM (tcgen05.mma ... [d_tmem], [a_tmem], b_desc): the queries never
+//     touch shared memory or L2 again, so on-chip traffic is the corpus stream only.
+//   * the corpus streams HBM -> TMA (128B-swizzled boxes of 64 elements x 32/64 rows) -> a 224 KB
+//     shared-memory ring -> tcgen05.mma as the B operand (64 rows per tile).
+//   * with two query tiles or more, x-adjacent CTAs form cta_group::2 PAIRS: each loads only its 32
+//     rows of a tile, the leader issues one M = 256 MMA per k-step for both tensor cores (MODE 2;
+//     MODE 1 is the older TMA-multicast pair, MODE 0 a single CTA).
+//   * accumulators: a ring of 64-column fp32 buffers at the top of TMEM (2 behind a 768-wide A
+//     operand, 4 when D <= 512).  Four epilogue warps drain a tile with tcgen05.ld (thread = one
+//     query, 64 scores), hand the buffer back, reject the whole tile with a 32-instruction
+//     three-input-max test against a bound shared by all CTAs of the query tile, and only otherwise
+//     walk the scores and insert survivors into a per-thread list (registers for k <= 16, a max-heap
+//     in local memory beyond).  live/filter bitmaps are applied on the survivor path; tiles whose 64
+//     rows are all dead or filtered are skipped by every role.
+//   * fp32 stores are contracted as bf16 hi/lo pairs (3 MMAs per k-step) and re-ranked exactly.
+//   * warp roles: 0 = TMA producer, 1 and 6 = MMA issuers on alternate tiles (1 owns the TMEM
+//     allocation), 2-5 = epilogue.
 //
-// Roofline: HBM for B <= ~256 (corpus read once, 2 x 128 x 64 x 16 MACs per 2 KB of
-// stage), tensor pipe beyond.  Algorithmic FLOPs = 2 B N D.
+// Roofline: HBM for B <= ~256 (corpus read once), tensor pipe beyond.  Algorithmic FLOPs = 2 B N D.
 #include "tensor_regime.h"
 
 #include <cuda.h>
