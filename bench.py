@@ -249,8 +249,10 @@ def main():
     for s in range(0, n_local, chunk):
         m = min(chunk, n_local - s)
         xs = torch.randn((m, args.dim), generator=gen, device=dev, dtype=torch.float32)
+        if args.space != "cosine":                 # unit-norm rows in every space (cosine stores normalise themselves)
+            xs = torch.nn.functional.normalize(xs, dim=1)
         torch.cuda.synchronize(dev)
-        store.upsert_device(xs.data_ptr(), m)      # K1 normalises + converts on the way in
+        store.upsert_device(xs.data_ptr(), m)      # K1 normalises (cosine) + converts on the way in
         del xs
     build_s = time.perf_counter() - t_build0
     assert store.count() == n_local

@@ -113,7 +113,7 @@ struct rag_store {
   int64_t live = 0;
   void* d_vectors = nullptr;
   float* d_norms2 = nullptr;
-  float* d_max_norm2 = nullptr;          // [1] largest |stored row|^2 ever written (error bound of the split regime)
+  float* d_max_norm2 = nullptr;          // [2] largest / smallest |stored row|^2 ever written (error bound of the split regime, l2 rejection bound)
   uint32_t* d_live = nullptr;
   // fp32 stores, tensor regime: bf16 [capacity][hi(row_elems) | lo(row_elems)] split of the rows, built on
   // the first large-batch query, kept in step by upsert, dropped (and rebuilt lazily) when the store grows
@@ -418,7 +418,7 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
   if (regime == 2) {
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     tensor::Problem p{};
-    p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.norms2 = s->d_norms2; p.n_rows = s->rows; p.row_elems = s->row_elems;
+    p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.norms2 = s->d_norms2; p.min_norm2 = s->d_max_norm2 + 1; p.n_rows = s->rows; p.row_elems = s->row_elems;
     p.dim = s->dim; p.dtype = s->dtype; p.space = s->space;
     p.live = s->d_live; p.filter = filter; p.filter_words = fwords;
     p.dense = (filter == nullptr && s->live == s->rows) ? 1 : 0;
@@ -595,8 +595,11 @@ int rag_store_create(int dim, int dtype, int space, int device, int64_t capacity
   e = cudaStreamCreateWithFlags(&s->admin.stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete s; return fail(RAG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   s->admin.own_stream = true;
-  e = cudaMalloc(reinterpret_cast<void**>(&s->d_max_norm2), sizeof(float));
-  if (e == cudaSuccess) e = cudaMemset(s->d_max_norm2, 0, sizeof(float));
+  e = cudaMalloc(reinterpret_cast<void**>(&s->d_max_norm2), 2 * sizeof(float));
+  if (e == cudaSuccess) {
+    const float init[2] = {0.0f, __builtin_inff()};      // [0] running max, [1] running min of |stored row|^2
+    e = cudaMemcpy(s->d_max_norm2, init, sizeof(init), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) { (void)cudaGetLastError(); rag_store_destroy(s); return fail(RAG_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
   s->tensor_plan = tensor::create_plan();
   int rc = grow(s, std::max<int64_t>(capacity_hint, 1024));

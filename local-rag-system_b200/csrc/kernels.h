@@ -121,7 +121,7 @@ struct UpsertArgs {
   int normalise;            // cosine
   void* vectors;
   float* norms2;            // [capacity] sum of squares of the stored row
-  float* max_norm2;         // [1] running maximum of norms2 over everything ever stored (error bounds)
+  float* max_norm2;         // [2] running maximum [0] and minimum [1] of norms2 over everything ever stored (error / rejection bounds)
   uint32_t* live;
   // optional split-precision shadow of an fp32 store for the tensor regime: row r is
   // [hi(row_elems) | lo(row_elems)] bf16 with x = hi + lo + O(2^-17 |x|); nullptr when absent

@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(kThreads) upsert_kernel(const UpsertArgs a) {
     const unsigned int bits = __float_as_uint(stored_ss);
     if (bits > *reinterpret_cast<volatile unsigned int*>(a.max_norm2))
       atomicMax(reinterpret_cast<unsigned int*>(a.max_norm2), bits);
+    if (bits < *reinterpret_cast<volatile unsigned int*>(a.max_norm2 + 1))
+      atomicMin(reinterpret_cast<unsigned int*>(a.max_norm2 + 1), bits);
   }
   if (lane == 0) {
     a.norms2[row] = stored_ss;

@@ -255,6 +255,7 @@ struct Args {
   const __nv_bfloat16* q_bf16;   // [n_mtiles*128][row_elems] prepared queries, zero rows beyond B
   const float* q_norm2;          // [n_mtiles*128]
   const float* x_norm2;          // [n_rows] (l2)
+  const float* x_min_norm2;      // [1] lower bound of x_norm2 over the store (l2)
   const uint32_t* live;
   const uint32_t* filter;
   int64_t filter_words;
@@ -265,6 +266,7 @@ struct Args {
   int dense;                     // 1: no filter and no tombstones -> tile masks are computed, not loaded
   int prefetch;                  // L2 prefetch distance in tiles (0 = off)
   int nbuf;                      // accumulator buffers in tensor memory (2 or 4)
+  int stages_used;               // ring stages in use (<= Ring<MODE>::kStages)
   int split_steps;               // > 0: split-precision rows [hi | lo], the first split_steps k-steps are hi
   uint64_t* partial;             // [cpm][B][k]
   // [n_mtiles*128] ordered(fp32): smallest k-th-best distance any CTA has reached for this query so far.
@@ -371,7 +373,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;             // 1024-byte aligned stage ring
-  const uint32_t bar_base = base + kStages * kStageBytes;
+  // ring stages in use: all of them, or a short ring when the per-thread top-k lists live in local memory
+  // (k > 16): 128 threads x 1 KB of lists must stay L1-resident, and a 227 KB carve-out leaves L1 ~28 KB
+  // (the depth of the ring does not limit the kernel: 4 stages measured as fast as 14)
+  const uint32_t n_ring = static_cast<uint32_t>(a.stages_used);
+  const uint32_t bar_base = base + n_ring * kStageBytes;
   // barrier layout (8 bytes each): full[kStages], empty[kStages], acc_full[2], acc_empty[2], tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
-    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), PAIR ? 1 : CL); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), PAIR ? 1 : CL); }   // (unused ones included)
     for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), PAIR ? 8 : 4); }
     mbar_init(aready_bar, 8);
     fence_barrier_init();
@@ -430,6 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       if (a.dense && !masks) { p0 = 1u; p1 = 0u; return; }
       if (a.dense) {
         const int64_t left = a.n_rows - t * kNB;
+        if (left >= kNB) { p0 = p1 = 0xffffffffu; return; }
         p0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
         p1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
         return;
@@ -490,6 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     uint64_t kth_key = kEmptyKey;
     uint32_t* tau_slot = a.tau_shared + (mt * kM + m);
     const float qn = (L2 && q_valid) ? a.q_norm2[b] : 0.0f;
+    const float base_n = L2 ? qn + __ldg(a.x_min_norm2) : 0.0f;
 
     uint32_t it = 0;
     TileWalker walk(a, cj, n_tiles);
@@ -499,12 +507,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
       ++it;
-      float xn0 = 0.0f, xn1 = 0.0f;
-      if constexpr (L2) {
-        const int64_t r0 = t * kNB + lane, r1 = r0 + 32;
-        xn0 = (r0 < a.n_rows) ? __ldg(a.x_norm2 + r0) : 0.0f;
-        xn1 = (r1 < a.n_rows) ? __ldg(a.x_norm2 + r1) : 0.0f;
-      }
       // every 8th tile: pick up the bound the sibling CTAs have published (the load overlaps the wait below)
       const bool refresh = q_valid && ((it & 7u) == 1u);
       uint32_t tg_bits = 0xFFFFFFFFu;
@@ -529,75 +531,83 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         else mbar_arrive(acce_bar(buf));
       }
       // Fast reject: once the lists have warmed up almost no tile holds a candidate for any of the
-      // warp's 32 queries.  The largest of the 64 dot products (32 three-input max instructions)
-      // is tested against a bound that no candidate can fall below; only if some lane passes does
-      // the warp take the exact per-score path below (~5x the instructions).
-      {
-        float mx[32];
+      // warp's 32 queries.  The largest of the 64 dot products (a tree of 32 three-input max
+      // instructions) is tested against a bound that no candidate can fall below; only if some lane
+      // passes does the warp go on, and then each lane DESCENDS the same tree (7 subtree maxima -> 22
+      // group maxima -> scores) to the few scores that pass instead of testing all 64.
+      float m32[11], n32[11];                        // maxima of groups of 3 scores (columns 0-31 / 32-63)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx[j] = __uint_as_float(vv[0][j]);
-        float m32[11];
+      for (int j = 0; j < 10; ++j)
+        m32[j] = fmax3(__uint_as_float(vv[0][3 * j]), __uint_as_float(vv[0][3 * j + 1]), __uint_as_float(vv[0][3 * j + 2]));
+      m32[10] = fmaxf(__uint_as_float(vv[0][30]), __uint_as_float(vv[0][31]));
 #pragma unroll
-        for (int j = 0; j < 10; ++j) m32[j] = fmax3(mx[3 * j], mx[3 * j + 1], mx[3 * j + 2]);
-        m32[10] = fmaxf(mx[30], mx[31]);
+      for (int j = 0; j < 10; ++j)
+        n32[j] = fmax3(__uint_as_float(vv[1][3 * j]), __uint_as_float(vv[1][3 * j + 1]), __uint_as_float(vv[1][3 * j + 2]));
+      n32[10] = fmaxf(__uint_as_float(vv[1][30]), __uint_as_float(vv[1][31]));
+      const float t0 = fmax3(m32[0], m32[1], m32[2]), t1 = fmax3(m32[3], m32[4], m32[5]);
+      const float t2 = fmax3(m32[6], m32[7], m32[8]), t3 = fmax3(m32[9], m32[10], n32[0]);
+      const float t4 = fmax3(n32[1], n32[2], n32[3]), t5 = fmax3(n32[4], n32[5], n32[6]);
+      const float t6 = fmax3(n32[7], n32[8], n32[9]);
+      const float best = fmax3(fmax3(t0, t1, t2), fmax3(t3, t4, t5), fmaxf(t6, n32[10]));
+      float lb;                                      // lower bound on the dot product of any candidate of this lane
+      if constexpr (L2) {
+        // d = |q|^2 + |x|^2 - 2 q.x <= tau  =>  q.x >= (|q|^2 + min|x|^2 - tau) / 2 (minus rounding slack),
+        // with min|x|^2 over everything the store ever held (tracked by the upsert kernel): no per-tile loads
+        lb = 0.5f * (base_n - tau) - 4e-7f * (fabsf(base_n) + fabsf(tau));
+      } else {
+        // cosine / ip: fl(1 - dot) <= tau implies dot >= 1 - tau - 2^-24
+        lb = (1.0f - tau) - 1.2e-7f;
+      }
+      if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
+      if constexpr (L2) {
+        // second-level reject with THIS tile's smallest |x|^2 (the store-wide minimum above is loose when the
+        // rows' norms vary; unit-norm embeddings never get further with it)
+        const int64_t r0 = t * kNB + lane, r1 = r0 + 32;
+        const float xn0 = (r0 < a.n_rows) ? __ldg(a.x_norm2 + r0) : __int_as_float(0x7f800000);
+        const float xn1 = (r1 < a.n_rows) ? __ldg(a.x_norm2 + r1) : __int_as_float(0x7f800000);
+        float xmin = fminf(xn0, xn1);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx[j] = __uint_as_float(vv[1][j]);
-        float n32[11];
-#pragma unroll
-        for (int j = 0; j < 10; ++j) n32[j] = fmax3(mx[3 * j], mx[3 * j + 1], mx[3 * j + 2]);
-        n32[10] = fmaxf(mx[30], mx[31]);
-        float t0 = fmax3(m32[0], m32[1], m32[2]), t1 = fmax3(m32[3], m32[4], m32[5]);
-        float t2 = fmax3(m32[6], m32[7], m32[8]), t3 = fmax3(m32[9], m32[10], n32[0]);
-        float t4 = fmax3(n32[1], n32[2], n32[3]), t5 = fmax3(n32[4], n32[5], n32[6]);
-        float t6 = fmax3(n32[7], n32[8], n32[9]);
-        const float best = fmax3(fmax3(t0, t1, t2), fmax3(t3, t4, t5), fmaxf(t6, n32[10]));
-        float bound;
-        if constexpr (L2) {
-          // d = |q|^2 + |x|^2 - 2 q.x <= tau  =>  q.x >= (|q|^2 + min|x|^2 - tau) / 2 (minus rounding slack)
-          float xmin = fminf(xn0, xn1);
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
-          const float base_n = qn + xmin;
-          bound = 0.5f * (base_n - tau) - 4e-7f * (fabsf(base_n) + fabsf(tau));
-        } else {
-          bound = (1.0f - tau) - 1.2e-7f;
+        for (int off = 16; off > 0; off >>= 1) xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
+        const float bn = qn + xmin;
+        lb = 0.5f * (bn - tau) - 4e-7f * (fabsf(bn) + fabsf(tau));
+        if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
+      }
+      // ---- descent: candidate bits of this lane (a superset; the key comparison below is the exact test) ----
+      uint32_t c0 = 0u, c1 = 0u;
+      if (q_valid && best >= lb) {
+#define RAG_GROUP(GMAX, CBITS, H, G)                                                              \
+        if ((GMAX) >= lb) {                                                                       \
+          if (__uint_as_float(vv[H][3 * (G)]) >= lb) CBITS |= 1u << (3 * (G));                     \
+          if (__uint_as_float(vv[H][3 * (G) + 1]) >= lb) CBITS |= 1u << (3 * (G) + 1);             \
+          if (3 * (G) + 2 < 32 && __uint_as_float(vv[H][(3 * (G) + 2) & 31]) >= lb) CBITS |= 1u << ((3 * (G) + 2) & 31); \
         }
-        if (!__any_sync(0xffffffffu, q_valid && best >= bound)) continue;
+        if (t0 >= lb) { RAG_GROUP(m32[0], c0, 0, 0) RAG_GROUP(m32[1], c0, 0, 1) RAG_GROUP(m32[2], c0, 0, 2) }
+        if (t1 >= lb) { RAG_GROUP(m32[3], c0, 0, 3) RAG_GROUP(m32[4], c0, 0, 4) RAG_GROUP(m32[5], c0, 0, 5) }
+        if (t2 >= lb) { RAG_GROUP(m32[6], c0, 0, 6) RAG_GROUP(m32[7], c0, 0, 7) RAG_GROUP(m32[8], c0, 0, 8) }
+        if (t3 >= lb) { RAG_GROUP(m32[9], c0, 0, 9) RAG_GROUP(m32[10], c0, 0, 10) RAG_GROUP(n32[0], c1, 1, 0) }
+        if (t4 >= lb) { RAG_GROUP(n32[1], c1, 1, 1) RAG_GROUP(n32[2], c1, 1, 2) RAG_GROUP(n32[3], c1, 1, 3) }
+        if (t5 >= lb) { RAG_GROUP(n32[4], c1, 1, 4) RAG_GROUP(n32[5], c1, 1, 5) RAG_GROUP(n32[6], c1, 1, 6) }
+        if (t6 >= lb) { RAG_GROUP(n32[7], c1, 1, 7) RAG_GROUP(n32[8], c1, 1, 8) RAG_GROUP(n32[9], c1, 1, 9) }
+        RAG_GROUP(n32[10], c1, 1, 10)
+#undef RAG_GROUP
+        c0 &= w0;                                    // live & filter bits of the tile's rows
+        c1 &= w1;
       }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const uint32_t* v = vv[half];
-        float d[32];
-        uint32_t cand = 0;
-        if constexpr (L2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xn = __shfl_sync(0xffffffffu, half ? xn1 : xn0, j);
-            d[j] = fmaf(-2.0f, __uint_as_float(v[j]), qn + xn);
-            cand |= (d[j] <= tau) ? (1u << j) : 0u;
-          }
-        } else {
-          // cosine / ip: d = 1 - dot <= tau is pre-filtered in dot space, one FSETP per score.
-          // fl(1 - dot) <= tau implies dot >= 1 - tau - 2^-24, so the test below never loses a
-          // candidate; survivors are re-checked exactly by key.
-          const float tdot = (1.0f - tau) - 1.2e-7f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            d[j] = __uint_as_float(v[j]);
-            cand |= (d[j] >= tdot) ? (1u << j) : 0u;
-          }
-        }
-        cand &= half ? w1 : w0;                      // live & filter bits of these 32 rows
-        if (!q_valid) cand = 0;
+        uint32_t cand = half ? c1 : c0;
         while (cand) {
           const int j = __ffs(cand) - 1;
           cand &= cand - 1;
-          float dj = 0.0f;
+          float sc = 0.0f;
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) dj = (jj == j) ? d[jj] : dj;
-          if (L2) dj = fmaxf(dj, 0.0f);
-          else dj = 1.0f - dj;
-          const uint64_t key = make_key(dj, static_cast<uint32_t>(t * kNB + half * 32 + j));
+          for (int jj = 0; jj < 32; ++jj) sc = (jj == j) ? __uint_as_float(v[jj]) : sc;
+          const uint32_t row = static_cast<uint32_t>(t * kNB + half * 32 + j);
+          float dj;
+          if constexpr (L2) dj = fmaxf(fmaf(-2.0f, sc, qn + __ldg(a.x_norm2 + row)), 0.0f);
+          else dj = 1.0f - sc;
+          const uint64_t key = make_key(dj, row);
           if (key < kth_key && dj <= tau_g) {
             top.insert(key, k);
             kth_key = top.kth(k);
@@ -685,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           }
         }
         __syncwarp();
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+        if (++s == n_ring) { s = 0; ph ^= 1u; }
       }
     }
     if (n_sib > 1 && crank == 0 && lane == 0)                 // finished: nobody should ever wait for this cluster
@@ -713,7 +723,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     };
     TileWalker walk(a, cj, (PAIR && crank != 0) ? 0 : n_tiles, false);     // the peer's MMA warps issue nothing
     const uint32_t issuer = (warp == kMmaWarpB) ? 1u : 0u;
-    const uint32_t n_ring = static_cast<uint32_t>(kStages);
     int64_t t;
     uint32_t w0, w1;
     while (walk.next(t, w0, w1)) {
@@ -781,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           }
         }
         __syncwarp();
-        if (++s == kStages) { s = 0; ph ^= 1u; }
+        if (++s == n_ring) { s = 0; ph ^= 1u; }
       }
     }
     tc_fence_before();
@@ -846,15 +855,27 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
 }
 
 template <int KL, bool L2, int MODE>
-cudaError_t launch_one(const CUtensorMap& tmap, const Args& a, dim3 grid, cudaStream_t st) {
+cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t st) {
   constexpr int CL = (MODE == 0) ? 1 : 2;
   auto kern = gemm_topk_kernel<KL, L2, MODE>;
+  // k <= 16: lists in registers, the whole 224 KB ring.  Larger k: lists in local memory -> a short ring
+  // (64-96 KB) and the rest of the SM's 256 KB left to L1
+  a.stages_used = Ring<MODE>::kStages;
+  if (KL > 16) a.stages_used = (MODE == 2) ? 4 : 3;
+  if (const char* ev = getenv("RAG_B200_TENSOR_STAGES")) {
+    const int v = atoi(ev);
+    if (v >= 2 && v <= Ring<MODE>::kStages) a.stages_used = v;
+  }
+  const int smem_bytes = a.stages_used * Ring<MODE>::kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           (KL > 16) ? (smem_bytes + 8 * 1024) * 100 / (228 * 1024) + 1 : 100);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -941,7 +962,7 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
   Args a{};
-  a.q_bf16 = q_bf16; a.q_norm2 = q_norm; a.x_norm2 = p.norms2;
+  a.q_bf16 = q_bf16; a.q_norm2 = q_norm; a.x_norm2 = p.norms2; a.x_min_norm2 = p.min_norm2;
   a.live = p.live; a.filter = p.filter; a.filter_words = p.filter_words;
   a.n_rows = p.n_rows; a.row_elems = width; a.B = p.B; a.k = kk; a.cpm = L.cpm; a.partial = part;
   a.split_steps = split ? p.row_elems / 16 : 0;

@@ -20,6 +20,7 @@ struct Problem {
   const void* vectors;      // [n_rows][row_elems] bf16 (or fp32 when `shadow` is streamed instead), row-major
   const void* shadow;       // fp32 stores: [n_rows][hi(row_elems) | lo(row_elems)] bf16 split of the rows
   const float* norms2;      // [n_rows] |x|^2 of the stored rows (l2 space)
+  const float* min_norm2;   // [1] lower bound of norms2 over everything the store ever held
   int64_t n_rows;
   int row_elems, dim, dtype, space;
   const uint32_t* live;

@@ -594,3 +594,32 @@ def test_single_shard_searcher_matches_store_query():
         s1.close()
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_tensor_regime_l2_rows_of_very_different_norms(dtype):
+    """l2 in the tensor regime rejects whole tiles with a bound built from the smallest |x|^2 the store
+    ever held: rows spanning four orders of magnitude in norm (and a zero row) must not be lost."""
+    n, dim, k, B = 9000, 128, 10, 140
+    rng = np.random.default_rng(81)
+    x = rng.standard_normal((n, dim)).astype(np.float32) * (10.0 ** rng.uniform(-2, 2, size=(n, 1))).astype(np.float32)
+    x[1234] = 0.0
+    q = rng.standard_normal((B, dim)).astype(np.float32) * (10.0 ** rng.uniform(-2, 1, size=(B, 1))).astype(np.float32)
+    q[0] = x[77] * 1.001
+    q[1] = 1e-3 * rng.standard_normal(dim).astype(np.float32)          # nearest neighbours: the tiny rows and the zero row
+    if dtype == "bf16":
+        x, q = round_to_bf16(x), round_to_bf16(q)
+    st = DeviceStore(dim, dtype, "l2")
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        assert st.last_query_info()["regime"] == "tensor"
+        rs, ds, cs = st.query(q, k, regime="stream")
+        assert np.array_equal(counts, cs)
+        # the two regimes rank by differently rounded distances; compare through the distances
+        assert np.allclose(dists, ds, rtol=2e-5, atol=1e-6 * float(np.max(np.abs(ds)) + 1.0))
+        assert np.mean(rows == rs) > 0.99
+        assert rows[0, 0] == 77 and 1234 in rows[1].tolist()
+    finally:
+        st.close()
