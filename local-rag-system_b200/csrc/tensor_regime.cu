@@ -34,6 +34,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -274,6 +276,12 @@ struct Args {
   // be in the global top-k, so publishing the bound lets every CTA reject with the tightest one
   // (an order of magnitude fewer list insertions at k = 100).  0xFFFFFFFF = nothing published yet.
   uint32_t* tau_shared;
+  // Quantile bound for large k (nullptr = off): [n_mtiles*128][cpm] ordered(fp32).  CTA c publishes the
+  // distance of its own q-th best row, q = ceil(k / cpm).  Every CTA then holds >= q rows at or below
+  // T = max_c(slot c), i.e. >= k rows globally: nothing beyond T can be in the global top-k.  T estimates the
+  // same quantile as the global k-th best, cpm times tighter than any single CTA's own k-th best above.
+  uint32_t* tau_q;
+  int tau_q_rank;                // q (1..8)
   // [cpm][gridDim.y] inverted tile counters (0xFFFFFFFF - tiles issued) of the clusters that walk the same
   // corpus tiles for different query tiles.  A cluster may run at most kPaceWindow tiles ahead of its slowest
   // sibling, so a tile fetched from DRAM by the first cluster is still in L2 when the others ask for it
@@ -496,6 +504,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     float tau_g = __int_as_float(0x7f800000);        // last shared bound seen
     uint64_t kth_key = kEmptyKey;
     uint32_t* tau_slot = a.tau_shared + (mt * kM + m);
+    float small[8];                                  // own 8 smallest distances, ascending (quantile bound, k > 16 only)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) small[i] = __int_as_float(0x7f800000);
+    float small_q = __int_as_float(0x7f800000);      // small[q - 1]
+    const bool use_q = (KL > 16) && a.tau_q != nullptr;
+    uint32_t* q_row = use_q ? a.tau_q + static_cast<size_t>(mt * kM + m) * a.cpm : nullptr;
     const float qn = (L2 && q_valid) ? a.q_norm2[b] : 0.0f;
     const float base_n = L2 ? qn + __ldg(a.x_min_norm2) : 0.0f;
 
@@ -516,6 +530,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       if (tg_bits != 0xFFFFFFFFu) {
         tau_g = fminf(tau_g, ordered_to_float(tg_bits));
         tau = fminf(tau, tau_g);
+      }
+      if constexpr (KL > 16) {
+        if (use_q && refresh) {                      // T = max over the CTAs' q-th best (all must have one)
+          uint32_t worst = 0u;
+          for (int c = 0; c < a.cpm; ++c) {
+            uint32_t v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q_row + c) : "memory");
+            worst = v > worst ? v : worst;
+          }
+          if (worst != 0xFFFFFFFFu) {
+            tau_g = fminf(tau_g, ordered_to_float(worst));
+            tau = fminf(tau, tau_g);
+          }
+        }
       }
       // both halves of the 64-column accumulator are requested back to back, then the buffer is
       // handed back to the MMA warp before any score is looked at
@@ -608,6 +636,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           if constexpr (L2) dj = fmaxf(fmaf(-2.0f, sc, qn + __ldg(a.x_norm2 + row)), 0.0f);
           else dj = 1.0f - sc;
           const uint64_t key = make_key(dj, row);
+          if constexpr (KL > 16) {
+            if (use_q && dj < small_q) {             // keep the own q smallest distances and publish the q-th
+              float x = dj;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float c = small[i]; const bool lt = x < c; small[i] = lt ? x : c; x = lt ? c : x; }
+              small_q = small[0];
+#pragma unroll
+              for (int i = 1; i < 8; ++i) small_q = (i == a.tau_q_rank - 1) ? small[i] : small_q;
+              if (small_q < __int_as_float(0x7f800000))
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q_row + cj), "r"(float_to_ordered(small_q)) : "memory");
+            }
+          }
           if (key < kth_key && dj <= tau_g) {
             top.insert(key, k);
             kth_key = top.kth(k);
@@ -827,7 +867,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
   int n_mtiles, cpm, cl, mode;
-  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_tau, off_prog, off_merged, total;
+  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
 };
 
 // row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
@@ -849,6 +889,7 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
   L.off_tau = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);      // directly behind `partial`: one memset
   L.off_prog = off; off += align256(static_cast<size_t>(L.cpm) * L.n_mtiles * 4);  // ... which also covers the pacing counters
+  L.off_tauq = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * L.cpm * 4);   // ... and the quantile bounds
   L.off_merged = off; off += align256(static_cast<size_t>(B) * k * 8);
   L.total = off;
   return L;
@@ -870,7 +911,7 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           (KL > 16) ? (smem_bytes + 8 * 1024) * 100 / (228 * 1024) + 1 : 100);
+                           (KL > 16) ? std::min(100, (smem_bytes + 8 * 1024) * 100 / (228 * 1024) + 1) : 100);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
@@ -989,7 +1030,11 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
     if (v <= 0) a.progress = nullptr;
     else if (v > 1) a.pace_window = static_cast<uint32_t>(v);
   }
-  e = cudaMemsetAsync(part, 0xFF, (L.off_prog - L.off_partial) + static_cast<size_t>(L.cpm) * L.n_mtiles * 4, st);
+  a.tau_q = nullptr;
+  a.tau_q_rank = (kk + L.cpm - 1) / L.cpm;
+  if (kk > 16 && L.cpm <= 32 && a.tau_q_rank <= 8 && !(getenv("RAG_B200_TENSOR_TAUQ") && atoi(getenv("RAG_B200_TENSOR_TAUQ")) == 0))
+    a.tau_q = reinterpret_cast<uint32_t*>(p.scratch + L.off_tauq);
+  e = cudaMemsetAsync(part, 0xFF, (L.off_tauq - L.off_partial) + static_cast<size_t>(L.n_mtiles) * kM * L.cpm * 4, st);
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm * L.cl, L.n_mtiles / L.cl, 1);
   const bool l2 = (p.space == 0);

@@ -623,3 +623,24 @@ def test_tensor_regime_l2_rows_of_very_different_norms(dtype):
         assert rows[0, 0] == 77 and 1234 in rows[1].tolist()
     finally:
         st.close()
+
+
+@pytest.mark.parametrize("space,k", [("cosine", 40), ("l2", 100), ("ip", 17)])
+def test_tensor_regime_large_k_many_queries(space, k):
+    """k > 16 with >= 5 query tiles: per-thread heaps in local memory, the short ring, and the quantile bound
+    (every CTA publishes its own ceil(k / cpm)-th best; the maximum bounds the global k-th best)."""
+    n, dim, B = 30_000, 128, 600
+    rng = np.random.default_rng(91 + k)
+    x = unit_rows(n, dim, 92) if space != "l2" else (unit_rows(n, dim, 92) * rng.uniform(0.5, 2.0, (n, 1)).astype(np.float32))
+    q = unit_rows(B, dim, 93)
+    q[:50] = x[rng.choice(n, 50, replace=False)] + 0.01 * rng.standard_normal((50, dim)).astype(np.float32)
+    x, q = round_to_bf16(prepare_corpus(space, x)), round_to_bf16(prepare_corpus(space, q))
+    st = DeviceStore(dim, "bf16", space)
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        assert st.last_query_info()["regime"] == "tensor"
+        check_against_oracle(space, "bf16", stored, q, k, rows, dists, counts, min_recall=0.999)
+    finally:
+        st.close()
