@@ -14,3 +14,5 @@ run --rows 10000000 --dim 384 --dtype f32 --batch 1 --steps 100 --warmup 5
 # config 5, one GPU's share: 25M x 384 bf16, B = 1024, top-100, l2
 run --rows 25000000 --dim 384 --dtype bf16 --space l2 --batch 1024 --k 100 --steps 10 --warmup 3
 run --rows 25000000 --dim 384 --dtype bf16 --space l2 --batch 1024 --k 10 --steps 10 --warmup 3
+# headline shape with k = 100
+run --batch 1024 --k 100 --steps 10 --warmup 3
