@@ -996,10 +996,18 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(width) * 2};
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kNB / L.cl)};
   const cuuint32_t estride[2] = {1, 1};
+  // 128-byte promotion = exactly the box row (64 bf16); 256 B fetched the neighbouring k-slice early and cost the
+  // HBM-bound small batches 4 % (10M x 768, B = 32: 2.565 -> 2.469 ms); no effect at B = 1024
+  CUtensorMapL2promotion l2promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (const char* ev = getenv("RAG_B200_TENSOR_L2PROMO")) {
+    const int v = atoi(ev);
+    l2promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }
   CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                             const_cast<void*>(split ? static_cast<const void*>(p.shadow) : p.vectors), gdim, gstride, box,
                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
   Args a{};
