@@ -1,6 +1,6 @@
 // K3 + K4: tensor-core search regime for large query batches.
 //
-// Replaces, for B > 3 queries (B > 8 on fp32 stores), the hnswlib graph walk / numpy brute force
+// Replaces, for B > 2 queries (B > 6 on fp32 stores), the hnswlib graph walk / numpy brute force
 // behind collection.query (api/app.py:544-549) with an exact dense contraction
 // Q[B x D] . X[N x D]^T on the 5th-generation tensor cores, with the top-k selection fused into
 // the epilogue so the B x N score matrix never exists.

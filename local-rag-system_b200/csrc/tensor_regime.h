@@ -7,12 +7,13 @@
 namespace rag {
 namespace tensor {
 
-// batches larger than this go to the tensor regime when it supports the store (measured on
-// B200, 10M x 768 bf16: stream 2.24 ms @ B=2, 2.68 ms @ B=4; tensor 2.5 ms for any B <= 128)
-constexpr int kStreamMaxBatch = 3;
-// fp32 stores: the exact stream kernel shares one corpus pass between 8 queries; beyond that the
-// split-precision contraction (one pass per 128 queries + exact re-ranking) wins
-constexpr int kStreamMaxBatchF32 = 8;
+// batches larger than this go to the tensor regime when it supports the store.  Measured on B200 with
+// tools/crossover.py (final round-1 kernels), 10M x 768 bf16: stream 2.07 / 2.24 / 3.09 ms at B = 1 / 2 / 3,
+// tensor 2.36-2.47 ms for any B <= 16
+constexpr int kStreamMaxBatch = 2;
+// fp32 stores (1M x 384): the exact stream kernel 0.21 / 0.27 / 0.38 / 0.41 ms at B = 1 / 4 / 6 / 8, the
+// split-precision contraction + exact re-ranking 0.35-0.40 ms for any B <= 16
+constexpr int kStreamMaxBatchF32 = 6;
 
 struct Plan;   // cached TMA descriptors etc. for one store
 
