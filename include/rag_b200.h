@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 1
+#define RAG_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -79,6 +79,15 @@ RAG_API int rag_device_count(void);
  *   api/app.py:89-91, scripts/build_index.py:15-17                          */
 RAG_API int rag_store_create(int dim, int dtype, int space, int device,
                      int64_t capacity_hint, rag_store** out);
+/* same with flags.  By default a bf16 store also keeps the un-rounded fp32 rows (normalised for
+ * cosine): searches rank the bf16 rows (the HBM-bound scan reads only those), keep k + 6..16
+ * candidates and re-rank them exactly against the fp32 plane with the un-rounded query, so a bf16
+ * store returns the hits and the fp32 distances of the reference's fp32 index (recall@k >= 0.999;
+ * ranking on bf16 alone gives ~0.993 on 1M unit-norm rows).  RAG_STORE_NO_RERANK drops the plane
+ * (2 bytes per element instead of 6) and with it that guarantee.                              */
+#define RAG_STORE_NO_RERANK 1
+RAG_API int rag_store_create_ex(int dim, int dtype, int space, int device,
+                        int64_t capacity_hint, int flags, rag_store** out);
 RAG_API int rag_store_destroy(rag_store* s);
 /* make room for at least `rows` rows without further reallocation */
 RAG_API int rag_store_reserve(rag_store* s, int64_t rows);
@@ -94,6 +103,11 @@ RAG_API int rag_store_reserve(rag_store* s, int64_t rows);
  * L2-normalised by the upsert kernel.                                        */
 RAG_API int rag_store_upsert(rag_store* s, int64_t n, const float* vectors,
                      const int64_t* rows, int64_t* out_rows);
+/* Calls of <= 64 rows -- the reference's pattern: one col.add per document (api/app.py:209-225), 1-5
+ * chunks per col.upsert (scripts/build_index.py:89-96) -- are parked in pinned host memory and reach the
+ * device as one copy + one launch when the next read arrives or 256 rows have piled up; counts, rows and
+ * liveness reflect them at once.  rag_store_flush() forces them down and waits.                      */
+RAG_API int rag_store_flush(rag_store* s);
 /* same, vectors already on the store's device (bulk load / synthetic data) */
 RAG_API int rag_store_upsert_dev(rag_store* s, int64_t n, const float* vectors_dev,
                          const int64_t* rows, int64_t* out_rows);
@@ -111,6 +125,7 @@ RAG_API int rag_store_dim(const rag_store* s);
 RAG_API int rag_store_dtype(const rag_store* s);
 RAG_API int rag_store_space(const rag_store* s);
 RAG_API int rag_store_device(const rag_store* s);
+RAG_API int rag_store_has_rerank(const rag_store* s);   /* 1: bf16 store with the fp32 re-ranking plane */
 /* 1 if row is live, 0 if dead / out of range */
 RAG_API int rag_store_is_live(const rag_store* s, int64_t row);
 /* number of engine kernels launched by this store since creation */
@@ -119,6 +134,8 @@ RAG_API int64_t rag_store_kernel_launches(const rag_store* s);
 /* read vectors back as fp32 (the stored values: normalised / bf16-rounded) --
  * Collection.get(include=["embeddings"])                                     */
 RAG_API int rag_store_fetch(rag_store* s, int64_t n, const int64_t* rows, float* out);
+/* the un-rounded fp32 rows where the store keeps them (RAG_STORE_NO_RERANK not set), else as above */
+RAG_API int rag_store_fetch_exact(rag_store* s, int64_t n, const int64_t* rows, float* out);
 
 /* -- `where` filters -----------------------------------------------------------
  * Collection.query(where=...) -- api/app.py:540-548.  The host compiles the
@@ -127,6 +144,12 @@ RAG_API int rag_store_fetch(rag_store* s, int64_t n, const int64_t* rows, float*
  * nbits may be smaller than the row count: missing rows do not pass.         */
 RAG_API int rag_store_set_mask(rag_store* s, int slot, const uint64_t* bits, int64_t nbits);
 RAG_API int rag_store_clear_mask(rag_store* s, int slot);
+/* keep a parked mask valid across writes: bit rows[i] := pass[i] (0 / 1) for the n rows a write touched
+ * (rows distinct; rows past the mask's end extend it, bits in between stay 0).  The reference interleaves
+ * col.add with filtered /search (api/app.py:209-225, 540-548): re-uploading N/8 bytes per query after
+ * every write is what this avoids.                                                                    */
+RAG_API int rag_store_patch_mask(rag_store* s, int slot, int64_t n, const int64_t* rows,
+                         const unsigned char* pass);
 
 /* -- search --------------------------------------------------------------------
  * Collection.query(query_embeddings, n_results, where)
@@ -191,6 +214,48 @@ RAG_API int rag_store_fused_ok(const rag_store* s, const rag_exchange* x, int B,
 RAG_API int rag_store_query_fused_dev(rag_store* s, rag_exchange* x, int B, const float* queries_dev, int k,
                               int mask_slot, int flags, uint32_t row_base, int64_t* out_rows_dev,
                               float* out_dists_dev, int32_t* out_counts_dev, void* stream);
+/* the same with HOST buffers, synchronous: pinned staging, H2D of the queries, the one fused launch,
+ * one D2H of rows | dists | counts, all on the exchange's own stream -- the whole multi-GPU query is one
+ * C call per rank (what Collection.query costs on N GPUs).  Fails with RAG_ECUDA if a peer timed out. */
+RAG_API int rag_store_query_fused(rag_store* s, rag_exchange* x, int B, const float* queries, int k,
+                          int mask_slot, int flags, uint32_t row_base, int64_t* out_rows,
+                          float* out_dists, int32_t* out_counts);
+
+/* -- one collection over several devices of ONE process ----------------------------------------
+ * The reference builds one in-process collection and queries it from FastAPI worker threads
+ * (api/app.py:87-91, api/routes/kb.py:173-206); this is the multi-GPU form of exactly that object
+ * (Collection metadata "b200:devices": "0-7").  Chunks of 1024 rows are dealt round-robin to one store
+ * per device, global rows stay dense, and every call below means what its rag_store_* namesake means,
+ * with GLOBAL rows.  Small batches on distinct, peer-connected devices are answered by one fused
+ * scan + exchange + merge launch per device, issued concurrently by resident worker threads; other
+ * batches (tensor regime, shards sharing a device, no peer access) by per-shard searches whose keys
+ * are gathered on the first device and merged there.  Either way the answer is bit-identical to one
+ * store holding all rows.  `devices` may repeat a device (logical shards; used by the tests).        */
+typedef struct rag_sharded rag_sharded;
+RAG_API int rag_sharded_create(int dim, int dtype, int space, int n_devices, const int* devices,
+                       int64_t capacity_hint, int flags, rag_sharded** out);
+RAG_API int rag_sharded_destroy(rag_sharded* s);
+RAG_API int rag_sharded_shards(const rag_sharded* s);
+RAG_API rag_store* rag_sharded_shard(rag_sharded* s, int g);       /* borrowed; for introspection */
+RAG_API int rag_sharded_fused(const rag_sharded* s);               /* 1: the one-launch path is available */
+RAG_API int64_t rag_sharded_count(const rag_sharded* s);
+RAG_API int64_t rag_sharded_rows(const rag_sharded* s);
+RAG_API int rag_sharded_is_live(const rag_sharded* s, int64_t row);
+RAG_API int rag_sharded_reserve(rag_sharded* s, int64_t rows);
+RAG_API int rag_sharded_flush(rag_sharded* s);
+RAG_API int rag_sharded_upsert(rag_sharded* s, int64_t n, const float* vectors, const int64_t* rows,
+                       int64_t* out_rows);
+RAG_API int rag_sharded_delete(rag_sharded* s, int64_t n, const int64_t* rows);
+RAG_API int rag_sharded_fetch(rag_sharded* s, int64_t n, const int64_t* rows, float* out, int exact);
+RAG_API int rag_sharded_set_mask(rag_sharded* s, int slot, const uint64_t* bits, int64_t nbits);
+RAG_API int rag_sharded_patch_mask(rag_sharded* s, int slot, int64_t n, const int64_t* rows,
+                           const unsigned char* pass);
+RAG_API int rag_sharded_clear_mask(rag_sharded* s, int slot);
+RAG_API int rag_sharded_query(rag_sharded* s, int B, const float* queries, int k, int mask_slot, int flags,
+                      int64_t* out_rows, float* out_dists, int32_t* out_counts);
+/* path: 1 = fused one-launch-per-device, 2 = per-shard search + gather + merge kernel */
+RAG_API int rag_sharded_last_query_info(const rag_sharded* s, float* kernel_ms, int* regime, int* launches,
+                                int* path);
 
 /* helpers to (de)compose keys on the host */
 RAG_API uint64_t rag_key_pack(float dist, uint32_t row);

@@ -6,9 +6,9 @@ The directory name carries a hyphen (repo convention); import it as
 root maps one onto the other.
 """
 from .collection import Client, Collection, EphemeralClient, PersistentClient  # noqa: F401
-from .engine import DeviceStore, merge_keys_device  # noqa: F401
+from .engine import DeviceStore, ShardedDeviceStore, merge_keys_device  # noqa: F401
 from . import embedding_functions  # noqa: F401
 
-__version__ = "0.1.0"
-__all__ = ["Client", "Collection", "EphemeralClient", "PersistentClient", "DeviceStore",
+__version__ = "0.2.0"
+__all__ = ["Client", "Collection", "EphemeralClient", "PersistentClient", "DeviceStore", "ShardedDeviceStore",
            "merge_keys_device", "embedding_functions"]

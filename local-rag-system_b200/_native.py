@@ -23,6 +23,8 @@ EMPTY_KEY = 0xFFFFFFFFFFFFFFFF
 MAX_K = 1024
 MAX_MASK_SLOTS = 16
 EXCHANGE_HANDLE_BYTES = 64
+STORE_NO_RERANK = 1
+ABI_VERSION = 2
 
 _p = C.c_void_p
 _i64p = C.POINTER(C.c_int64)
@@ -36,9 +38,11 @@ SIGNATURES = {
     "rag_abi_version": (C.c_int, []),
     "rag_device_count": (C.c_int, []),
     "rag_store_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_p)]),
+    "rag_store_create_ex": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(_p)]),
     "rag_store_destroy": (C.c_int, [_p]),
     "rag_store_reserve": (C.c_int, [_p, C.c_int64]),
     "rag_store_upsert": (C.c_int, [_p, C.c_int64, _p, _p, _p]),
+    "rag_store_flush": (C.c_int, [_p]),
     "rag_store_upsert_dev": (C.c_int, [_p, C.c_int64, _p, _p, _p]),
     "rag_store_delete": (C.c_int, [_p, C.c_int64, _p]),
     "rag_store_count": (C.c_int64, [_p]),
@@ -48,9 +52,12 @@ SIGNATURES = {
     "rag_store_dtype": (C.c_int, [_p]),
     "rag_store_space": (C.c_int, [_p]),
     "rag_store_device": (C.c_int, [_p]),
+    "rag_store_has_rerank": (C.c_int, [_p]),
     "rag_store_is_live": (C.c_int, [_p, C.c_int64]),
     "rag_store_kernel_launches": (C.c_int64, [_p]),
     "rag_store_fetch": (C.c_int, [_p, C.c_int64, _p, _p]),
+    "rag_store_fetch_exact": (C.c_int, [_p, C.c_int64, _p, _p]),
+    "rag_store_patch_mask": (C.c_int, [_p, C.c_int, C.c_int64, _p, _p]),
     "rag_store_set_mask": (C.c_int, [_p, C.c_int, _p, C.c_int64]),
     "rag_store_clear_mask": (C.c_int, [_p, C.c_int]),
     "rag_store_query": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
@@ -63,6 +70,25 @@ SIGNATURES = {
     "rag_exchange_destroy": (C.c_int, [_p]),
     "rag_store_fused_ok": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int]),
     "rag_store_query_fused_dev": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p, _p]),
+    "rag_store_query_fused": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p]),
+    "rag_sharded_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int64, C.c_int, C.POINTER(_p)]),
+    "rag_sharded_destroy": (C.c_int, [_p]),
+    "rag_sharded_shards": (C.c_int, [_p]),
+    "rag_sharded_shard": (_p, [_p, C.c_int]),
+    "rag_sharded_fused": (C.c_int, [_p]),
+    "rag_sharded_count": (C.c_int64, [_p]),
+    "rag_sharded_rows": (C.c_int64, [_p]),
+    "rag_sharded_is_live": (C.c_int, [_p, C.c_int64]),
+    "rag_sharded_reserve": (C.c_int, [_p, C.c_int64]),
+    "rag_sharded_flush": (C.c_int, [_p]),
+    "rag_sharded_upsert": (C.c_int, [_p, C.c_int64, _p, _p, _p]),
+    "rag_sharded_delete": (C.c_int, [_p, C.c_int64, _p]),
+    "rag_sharded_fetch": (C.c_int, [_p, C.c_int64, _p, _p, C.c_int]),
+    "rag_sharded_set_mask": (C.c_int, [_p, C.c_int, _p, C.c_int64]),
+    "rag_sharded_patch_mask": (C.c_int, [_p, C.c_int, C.c_int64, _p, _p]),
+    "rag_sharded_clear_mask": (C.c_int, [_p, C.c_int]),
+    "rag_sharded_query": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
+    "rag_sharded_last_query_info": (C.c_int, [_p, _f32p, _i32p, _i32p, _i32p]),
     "rag_key_pack": (C.c_uint64, [C.c_float, C.c_uint32]),
     "rag_key_dist": (C.c_float, [C.c_uint64]),
     "rag_key_row": (C.c_uint32, [C.c_uint64]),
@@ -91,7 +117,7 @@ def load():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.rag_abi_version() != 1:
+    if lib.rag_abi_version() != ABI_VERSION:
         raise EngineError(f"ABI version mismatch: library reports {lib.rag_abi_version()}")
     _lib = lib
     return lib

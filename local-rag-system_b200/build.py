@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librag_b200.so")
-SOURCES = ["api.cu", "scan_stream.cu", "merge.cu", "store_kernels.cu", "tensor_regime.cu"]
+SOURCES = ["api.cu", "sharded.cu", "scan_stream.cu", "merge.cu", "store_kernels.cu", "tensor_regime.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

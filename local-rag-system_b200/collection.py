@@ -23,9 +23,9 @@ from typing import Any, Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from .engine import DeviceStore
-from .where import (MetadataColumns, evaluate_where_document, kind_of, validate_where,
-                    validate_where_document)
+from .engine import DeviceStore, ShardedDeviceStore
+from .where import (MetadataColumns, evaluate_where_document, kind_of, match_document, match_record,
+                    validate_where, validate_where_document)
 
 logger = logging.getLogger("local_rag_system_b200")
 
@@ -115,16 +115,21 @@ class _CollectionState:
         # where -> device mask slot cache
         self.mask_mu = threading.Lock()
         self.mask_slots: Dict[str, int] = {}       # canonical where -> slot
-        self.mask_version: Dict[int, int] = {}
+        self.mask_pred: Dict[str, tuple] = {}      # canonical where -> (where, where_document)
+        self.mask_valid: Dict[int, bool] = {}      # slot -> the device bitmap reflects every write so far
         self.mask_pins: Dict[int, int] = {}
         self.mask_lru: List[str] = []
         self.meta_version = 0
+        self.mask_uploads = 0                       # full bitmap evaluations + uploads (tests / diagnostics)
+        self.mask_patches = 0                       # incremental updates
         self.journal = None                         # persistence hook (persist.py)
 
     def apply_metadata(self, metadata: Optional[dict]):
         """Collection metadata carries the engine knobs: Chroma's `hnsw:space`
         (l2 | cosine | ip; default l2 as in the reference, api/app.py:91) plus
-        b200:dtype (f32 | bf16), b200:device, b200:capacity."""
+        b200:dtype (f32 | bf16), b200:device, b200:devices ("0-7" / "0,2,4" / [0, 1]: one
+        collection sharded over several GPUs of this process), b200:capacity,
+        b200:rerank ("f32" default | "none": bf16 stores keep / drop the fp32 re-ranking plane)."""
         self.metadata = dict(metadata) if metadata else None
         md = self.metadata or {}
         self.space = str(md.get("hnsw:space", os.environ.get("RAG_B200_SPACE", "l2")))
@@ -134,17 +139,47 @@ class _CollectionState:
         if self.dtype not in N.DTYPES:
             raise ValueError(f"b200:dtype must be f32 or bf16, got {self.dtype!r}")
         self.device = int(md.get("b200:device", os.environ.get("RAG_B200_DEVICE", "0")))
+        self.devices = _parse_devices(md.get("b200:devices", os.environ.get("RAG_B200_DEVICES")))
         self.capacity_hint = int(md.get("b200:capacity", 0))
+        rr = md.get("b200:rerank", os.environ.get("RAG_B200_RERANK"))
+        self.rerank = None if rr is None else str(rr).lower() not in ("0", "none", "off", "false")
 
     def ensure_store(self, dim: int):
         if self.store is None:
-            self.store = DeviceStore(dim, self.dtype, self.space, self.device, self.capacity_hint)
+            if self.devices and len(self.devices) > 1:
+                self.store = ShardedDeviceStore(dim, self.dtype, self.space, self.devices, self.capacity_hint, self.rerank)
+            else:
+                dev = self.devices[0] if self.devices else self.device
+                self.store = DeviceStore(dim, self.dtype, self.space, dev, self.capacity_hint, self.rerank)
             self.dim = dim
         elif dim != self.dim:
             raise ValueError(f"Embedding dimension {dim} does not match collection dimensionality {self.dim}")
 
     def n_rows(self) -> int:
         return 0 if self.store is None else self.store.rows()
+
+
+def _parse_devices(spec):
+    """"0-7" | "0,2,4" | "0-3,6" | [0, 1] | 3 -> list of device ordinals (None when unset)."""
+    if spec is None or spec == "":
+        return None
+    if isinstance(spec, (int, np.integer)):
+        return [int(spec)]
+    if isinstance(spec, (list, tuple)):
+        return [int(d) for d in spec]
+    out: List[int] = []
+    for part in str(spec).split(","):
+        part = part.strip()
+        if not part:
+            continue
+        if "-" in part:
+            lo, hi = part.split("-", 1)
+            out.extend(range(int(lo), int(hi) + 1))
+        else:
+            out.append(int(part))
+    if not out:
+        raise ValueError(f"b200:devices must name at least one device, got {spec!r}")
+    return out
 
 
 def _validate_metadata(m):
@@ -221,6 +256,8 @@ class Collection:
         docs = list(documents) if documents is not None else [None] * n
         return ids, np.ascontiguousarray(emb), metas, docs
 
+    _PATCH_MAX_ROWS = 4096      # larger writes re-evaluate the predicate instead of patching row by row
+
     def _write_rows(self, s: _CollectionState, rows: np.ndarray, ids, metas, docs):
         top = int(rows.max()) + 1
         s.ids, s.docs, s.metas = _grow_obj(s.ids, top), _grow_obj(s.docs, top), _grow_obj(s.metas, top)
@@ -229,6 +266,28 @@ class Collection:
             s.ids[r], s.docs[r], s.metas[r] = i, d, m
             s.row_of[i] = r
         s.meta_version += 1
+        self._patch_masks(s, rows)
+
+    def _patch_masks(self, s: _CollectionState, rows: np.ndarray):
+        """Keep the cached `where` bitmaps valid across a write: only the written rows' bits change
+        (api/app.py interleaves col.add with filtered /search; re-evaluating the predicate over every
+        row and re-uploading N/8 bytes per query after each write is what this avoids)."""
+        with s.mask_mu:
+            if not s.mask_slots:
+                return
+            if rows.size > self._PATCH_MAX_ROWS:
+                for slot in s.mask_slots.values():
+                    s.mask_valid[slot] = False
+                return
+            rl = rows.tolist()
+            for key, slot in s.mask_slots.items():
+                if not s.mask_valid.get(slot):
+                    continue
+                where, wd = s.mask_pred[key]
+                passing = np.fromiter((match_record(where, s.metas[r]) and match_document(wd, s.docs[r]) for r in rl),
+                                      dtype=np.uint8, count=len(rl))
+                s.store.patch_mask(slot, rows, passing)
+                s.mask_patches += 1
 
     # ----------------------------------------------------------------- writes
     def add(self, ids, embeddings=None, metadatas=None, documents=None, uris=None, images=None):
@@ -251,12 +310,26 @@ class Collection:
                 s.journal.log("add", sel_ids, emb[keep], [metas[j] for j in keep], [docs[j] for j in keep])
 
     def upsert(self, ids, embeddings=None, metadatas=None, documents=None, uris=None, images=None):
-        """Insert or replace in place.  Reference: scripts/build_index.py:92-96."""
+        """Insert, or update in place.  Reference: scripts/build_index.py:92-96.  For an id that
+        exists the vector is replaced and -- as Chroma's metadata segment does for an UPSERT record
+        (SqliteMetadataSegment._update_metadata: keys given are inserted-or-replaced, keys not given
+        stay; the document is the key "chroma:document") -- metadata keys are MERGED and the document is
+        kept when the call passes none."""
+        had_docs = documents is not None
         ids, emb, metas, docs = self._prepare_records(ids, embeddings, metadatas, documents)
         s = self._s
         with _Exclusive(s.rw):
             s.ensure_store(emb.shape[1])
             want = np.array([s.row_of.get(i, -1) for i in ids], dtype=np.int64)
+            for j, r in enumerate(want.tolist()):
+                if r < 0:
+                    continue
+                if s.metas[r]:
+                    merged = dict(s.metas[r])
+                    merged.update(metas[j] or {})
+                    metas[j] = merged
+                if not had_docs:
+                    docs[j] = s.docs[r]
             rows = s.store.upsert(emb, want)
             self._write_rows(s, rows, ids, metas, docs)
             if s.journal is not None:
@@ -293,8 +366,9 @@ class Collection:
                 if documents is not None:
                     s.docs[r] = documents[j]
             s.meta_version += 1
+            self._patch_masks(s, rows)
             if s.journal is not None:
-                vec = s.store.fetch(rows) if emb is None else emb
+                vec = s.store.fetch(rows, exact=True) if emb is None else emb
                 s.journal.log("upsert", [ids_l[j] for j in known], vec, [s.metas[int(r)] for r in rows],
                               [s.docs[int(r)] for r in rows])
 
@@ -344,11 +418,12 @@ class Collection:
         return 0 if s.store is None else s.store.count()
 
     def _mask_slot(self, s: _CollectionState, where, where_document) -> int:
-        """Resolve a predicate to a pinned device mask slot (compile + upload on miss)."""
+        """Resolve a predicate to a pinned device mask slot (compile + upload on a miss; a hit costs a
+        dictionary look-up: writes patch the cached bitmaps in place, see _patch_masks)."""
         key = json.dumps([where or None, where_document or None], sort_keys=True, ensure_ascii=False, default=str)
         with s.mask_mu:
             slot = s.mask_slots.get(key)
-            if slot is not None and s.mask_version.get(slot) == s.meta_version:
+            if slot is not None and s.mask_valid.get(slot):
                 s.mask_pins[slot] = s.mask_pins.get(slot, 0) + 1
                 s.mask_lru.remove(key)
                 s.mask_lru.append(key)
@@ -363,6 +438,7 @@ class Collection:
                     if victim is None:
                         raise RuntimeError("all filter slots are in use by concurrent queries")
                     slot = s.mask_slots.pop(victim)
+                    s.mask_pred.pop(victim, None)
                     s.mask_lru.remove(victim)
             elif s.mask_pins.get(slot, 0) != 0:
                 raise RuntimeError("filter slot busy")   # cannot happen: writers exclude readers
@@ -371,8 +447,10 @@ class Collection:
             if where_document:
                 passing &= evaluate_where_document(where_document, s.docs, n)
             s.store.set_mask(slot, passing)
+            s.mask_uploads += 1
             s.mask_slots[key] = slot
-            s.mask_version[slot] = s.meta_version
+            s.mask_pred[key] = (where or None, where_document or None)
+            s.mask_valid[slot] = True
             if key in s.mask_lru:
                 s.mask_lru.remove(key)
             s.mask_lru.append(key)
@@ -448,7 +526,7 @@ class Collection:
                 if out["documents"] is not None:
                     out["documents"][b] = s.docs[r].tolist()
                 if out["embeddings"] is not None:
-                    out["embeddings"][b] = s.store.fetch(r).tolist() if r.size else []
+                    out["embeddings"][b] = s.store.fetch(r, exact=True).tolist() if r.size else []
             return out
 
     def get(self, ids=None, where=None, limit=None, offset=None, where_document=None,
@@ -483,7 +561,7 @@ class Collection:
             if "documents" in include:
                 out["documents"] = s.docs[rows].tolist() if rows.size else []
             if "embeddings" in include:
-                out["embeddings"] = s.store.fetch(rows).tolist() if rows.size else []
+                out["embeddings"] = s.store.fetch(rows, exact=True).tolist() if rows.size else []
             return out
 
     def peek(self, limit: int = 10):

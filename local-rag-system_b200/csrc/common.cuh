@@ -40,6 +40,29 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) {
   return static_cast<uint32_t>(k & 0xFFFFFFFFull);
 }
 
+// ---- local row -> global row --------------------------------------------------------------
+// A shard emits keys whose row field is the GLOBAL row, so a cross-shard merge is a plain 64-bit
+// compare.  Two placements:
+//   contiguous (shift == 0): global = local + base                    one process per GPU, rank g owns
+//                                                                     [g * stride, g * stride + rows_g)
+//   striped    (shift  > 0): chunks of 2^shift rows dealt round-robin to `world` shards; shard g holds
+//                            chunks g, g + world, ...; base = g << shift:
+//                            global = ((local >> shift) * world << shift) + base + (local & (2^shift - 1))
+//                            (the single-process multi-device store: global rows stay dense while every
+//                            shard grows at the same rate)
+struct RowMap {
+  uint32_t base;
+  uint32_t shift;
+  uint32_t world;
+};
+__host__ __device__ __forceinline__ uint32_t to_global_row(const RowMap m, uint32_t local) {
+  if (m.shift == 0u) return local + m.base;
+  return (((local >> m.shift) * m.world) << m.shift) + m.base + (local & ((1u << m.shift) - 1u));
+}
+__host__ __device__ __forceinline__ uint64_t key_to_global(const RowMap m, uint64_t key) {
+  return (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(to_global_row(m, static_cast<uint32_t>(key)));
+}
+
 __host__ __device__ __forceinline__ int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;

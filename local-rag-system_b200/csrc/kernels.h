@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace rag {
 
 constexpr int kScanThreads = 256;             // 8 warps per CTA
@@ -24,15 +26,21 @@ struct ScanArgs {
   const float* queries_raw; // [B][dim] raw fp32: the kernel normalises / rounds them itself (saves a launch)
   int dim, normalise, round_bf16;
   int B;
-  int k;
+  int k;                    // list length kept per query during the scan
+  int k_out;                // hits emitted per query (<= k; < k only with the exact re-ranking below)
   int l2;                   // 1: d = sum((q-x)^2), 0: d = 1 - q.x
   int grid_x;
+  // Exact fp32 re-ranking (bf16 stores with an fp32 plane; nullptr = off): the k best rows
+  // by stored-precision distance are re-scored against the un-rounded fp32 rows with the un-rounded
+  // query, re-sorted, and the best k_out emitted.  Needs queries_raw (the fused single-launch mode).
+  const float* exact;       // [rows][exact_elems] fp32 (normalised for cosine stores)
+  int exact_elems;          // row pitch of `exact` in floats (dim padded to 4)
   // fused cross-CTA merge: every CTA publishes its sorted top-k, the LAST CTA of a query
   // group to finish (atomic ticket) merges all of them and emits the final result.
   uint64_t* partial;        // [grid_x][B][k] keys (ascending per list)
   unsigned int* done;       // [ceil(B / QB)] tickets, zero on entry; the last CTA re-zeroes its ticket
   int merge_keys_cap;       // keys of dynamic shared memory usable by the final in-smem sort (power of two)
-  uint32_t row_base;        // added to emitted rows (multi-GPU: this shard's first global row)
+  RowMap rows_map;          // local -> global row of emitted hits (multi-GPU: this shard's placement)
   uint64_t* out_keys;       // [B][k] or nullptr
   int64_t* out_rows;        // [B][k] or nullptr
   float* out_dists;         // [B][k] or nullptr
@@ -77,7 +85,7 @@ int scan_stream_groups(int B, int dtype, int row_elems, int k);
 struct MergeArgs {
   const uint64_t* keys;     // [S][B][k]
   int S, B, k;
-  uint32_t row_base;        // added to the row field of emitted keys
+  RowMap rows_map;          // local -> global row of emitted keys
   uint64_t* out_keys;       // [B][k] or nullptr
   int64_t* out_rows;        // [B][k] or nullptr
   float* out_dists;         // [B][k] or nullptr
@@ -89,8 +97,8 @@ cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st);
 struct RefineArgs {
   const uint64_t* keys;     // [B][k_in] merged winners (rows local to the store)
   const void* vectors;
-  const float* queries;     // [B][row_elems] prepared fp32
-  int dtype, row_elems, B, k;
+  const float* queries;     // [B][row_elems] prepared fp32 (same pitch as the rows re-scored)
+  int dtype, row_elems, B, k;   // dtype / row_elems describe `vectors` (the fp32 plane of a bf16 store: dtype 0)
   int k_in;                 // candidates per query (>= k)
   int l2;                   // 1: sum((q-x)^2), 0: 1 - q.x
   // exactness guard of the split-precision regime (nullptr = off): the candidates were ranked by
@@ -103,7 +111,7 @@ struct RefineArgs {
   const float* x_max_norm2; // [1]
   int* redo_count;
   int* redo_list;
-  uint32_t row_base;
+  RowMap rows_map;
   uint64_t* out_keys;
   int64_t* out_rows;
   float* out_dists;
@@ -123,6 +131,9 @@ struct UpsertArgs {
   float* norms2;            // [capacity] sum of squares of the stored row
   float* max_norm2;         // [2] running maximum [0] and minimum [1] of norms2 over everything ever stored (error / rejection bounds)
   uint32_t* live;
+  // optional un-rounded fp32 plane of a bf16 store (exact re-ranking): [capacity][exact_elems]; nullptr when absent
+  float* exact;
+  int exact_elems;
   // optional split-precision shadow of an fp32 store for the tensor regime: row r is
   // [hi(row_elems) | lo(row_elems)] bf16 with x = hi + lo + O(2^-17 |x|); nullptr when absent
   __nv_bfloat16* shadow;
@@ -142,6 +153,8 @@ struct PrepArgs {
   int normalise, round_bf16;
   int split;                // 1: q_bf16 rows are [hi(row_elems) | lo(row_elems)] (fp32 stores, tensor regime)
   float* q_f32;             // [B][row_elems]
+  float* q_exact;           // [B][exact_elems] normalised but NOT rounded (exact re-ranking of bf16 stores) or nullptr
+  int exact_elems;
   __nv_bfloat16* q_bf16;    // [Bpad][row_elems * (split ? 2 : 1)] or nullptr (rows >= B zero-filled by caller)
   float* q_norm2;           // [B] or nullptr
   // optional initialisation of the scan kernel's merge state (done here to save launches)
@@ -151,6 +164,10 @@ struct PrepArgs {
   int64_t init_zero_n;
 };
 cudaError_t launch_prep_queries(const PrepArgs& a, cudaStream_t st);
+
+// set / clear single bits of a `where` bitmap: bit rows[i] := pass[i] (rows are distinct within a call)
+cudaError_t launch_patch_mask(uint32_t* mask, const int64_t* rows_dev, const unsigned char* pass_dev, int64_t n,
+                              cudaStream_t st);
 
 // fetch rows back as fp32
 cudaError_t launch_fetch(const void* vectors, int dtype, int dim, int row_elems,

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const MergeArgs a)
     uint64_t key = lists[j];
     const bool valid = key != kEmptyKey;
     if (valid) {
-      key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+      key = key_to_global(a.rows_map, key);
       cnt++;
     }
     const size_t o = static_cast<size_t>(b) * k + j;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_small_kernel(const MergeA
     }
     if (lane == 0) {
       uint64_t key = m;
-      if (valid) key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+      if (valid) key = key_to_global(a.rows_map, key);
       const size_t o = static_cast<size_t>(b) * k + r;
       if (a.out_keys) a.out_keys[o] = key;
       if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kMergeThreads) refine_kernel(const RefineArgs 
     uint64_t key = keys[j];
     const bool valid = key != kEmptyKey;
     if (valid) {
-      key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+      key = key_to_global(a.rows_map, key);
       cnt++;
     }
     const size_t o = static_cast<size_t>(b) * k + j;

@@ -278,8 +278,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     // bitmap load per block.  Here lanes 0..7 fetch the 8 bitmap words of a chunk at once (the
     // next chunk's words are requested before this one is processed), a warp scan ranks the set
     // bits, and every step fills all R x G slots with the next passing rows of the chunk.
-    constexpr int CW = 8;                               // bitmap words per chunk
-    constexpr int kGatherMaxRows = 64;                  // gather when <= 25 % of the chunk's rows pass
+    constexpr int CW = 16;                              // bitmap words per chunk (512 rows)
+    constexpr int kGatherMaxRows = CW * 32 / 4;         // gather when <= 25 % of the chunk's rows pass
+    __shared__ uint16_t s_pass[kScanWarps][kGatherMaxRows];   // per warp: offsets of the chunk's passing rows
     const int64_t nchunk = (nblk + CW - 1) / CW;
     auto fetch_words = [&](int64_t chunk) -> uint32_t {
       const int64_t w = chunk * CW + lane;
@@ -300,8 +301,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         if (lane >= off) incl += o;
       }
       const int T = __shfl_sync(0xffffffffu, incl, CW - 1);   // lanes >= CW hold word = 0
-      if (lane >= CW) incl = T;
-      const int excl = incl - pop;
+      if (T == 0) continue;
       const uint4* cbase = vec + static_cast<size_t>(chunk) * (CW * kRowsPerBlock) * cpr;
       if (T > kGatherMaxRows) {
         // well-filled chunk: block by block as in the dense walk (cheaper row selection, rows
@@ -327,26 +327,30 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         }
         continue;
       }
+      // sparse chunk: every lane appends the offsets of its word's set bits to the warp's list (ranks
+      // from the prefix scan), then each step fills all R x G row slots from the list with one
+      // shared-memory read per slot.  (An earlier version located the j-th set bit per slot with
+      // ballot + shuffle + __fns: ~70 instructions per slot, 2/3 of the kernel's issue slots at 10 %.)
+      {
+        uint32_t m = word;
+        int pos = incl - pop;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= (m - 1);
+          s_pass[warp][pos++] = static_cast<uint16_t>(lane * kRowsPerBlock + bit);
+        }
+      }
+      __syncwarp();
       for (int j0 = 0; j0 < T; j0 += R * G) {
         int r[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-          r[i] = -1;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const int j = j0 + i * G + g;               // rank of the passing row that goes into slot (i, g)
-            int row = -1;
-            if (j < T) {
-              const int wl = __popc(__ballot_sync(0xffffffffu, incl <= j));   // word holding the j-th set bit
-              const int nth = j - __shfl_sync(0xffffffffu, excl, wl);
-              const uint32_t wd = __shfl_sync(0xffffffffu, word, wl);
-              row = wl * kRowsPerBlock + static_cast<int>(__fns(wd, 0u, nth + 1));
-            }
-            if (G == 1 || g == grp) r[i] = row;
-          }
+          const int j = j0 + i * G + grp;              // rank of the passing row that goes into this lane's slot i
+          r[i] = (j < T) ? static_cast<int>(s_pass[warp][j]) : -1;
         }
         process(cbase, chunk * (CW * kRowsPerBlock), r);
       }
+      __syncwarp();                                     // the list is rewritten for the next chunk
     }
   }
 
@@ -384,6 +388,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
 
   const int S = gridDim.x;
   const int total = S * k;
+  const int ko = a.k_out;                                      // hits emitted per query (k_out <= k)
   uint64_t* pool = reinterpret_cast<uint64_t*>(smem_raw);      // queries / lists are dead now
 #pragma unroll 1
   for (int qb = 0; qb < QB; ++qb) {
@@ -490,30 +495,59 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       block_bitonic_sort(pool, kScanWarps * kpad);
       sorted = pool;
     }
+    if (a.exact != nullptr) {
+      // ---- exact fp32 re-ranking (bf16 store with an fp32 plane) ---------------------------------
+      // `sorted` holds the k best rows by STORED-precision distance.  Re-score them against the
+      // un-rounded fp32 rows with the un-rounded (normalised) query -- one warp per candidate; slot j
+      // is read and rewritten only by warp j % 8 -- then sort again; the best k_out are emitted.
+      __syncthreads();
+      const int bs_q = a.q_index ? a.q_index[b] : b;
+      const float* qraw = a.queries_raw + static_cast<size_t>(bs_q) * a.dim;
+      const float qscale = s_scale[qb];
+      for (int j = warp; j < k; j += kScanWarps) {
+        const uint64_t key = sorted[j];
+        if (key == kEmptyKey) continue;
+        const uint32_t row = key_row(key);
+        const float* xr = a.exact + static_cast<size_t>(row) * a.exact_elems;
+        float acc = 0.0f;
+        for (int e = lane; e < a.dim; e += 32) {
+          const float qv = qraw[e] * qscale;
+          const float xv = __ldg(xr + e);
+          if constexpr (L2) { const float d = xv - qv; acc = fmaf(d, d, acc); }
+          else acc = fmaf(xv, qv, acc);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) sorted[j] = make_key(L2 ? acc : 1.0f - acc, row);
+      }
+      __syncthreads();
+      for (int j = k + threadIdx.x; j < kpad; j += blockDim.x) sorted[j] = kEmptyKey;
+      block_bitonic_sort(sorted, kpad);
+    }
     if (a.xchg_peers != nullptr) {
       // publish this shard's list of query b into the slot [parity][my rank] of EVERY rank's buffer
       const int par = static_cast<int>(a.xchg_epoch & 1u);
-      for (int idx = threadIdx.x; idx < a.xchg_world * k; idx += blockDim.x) {
-        const int g = idx / k, j = idx - g * k;
+      for (int idx = threadIdx.x; idx < a.xchg_world * ko; idx += blockDim.x) {
+        const int g = idx / ko, j = idx - g * ko;
         uint64_t key = sorted[j];
-        if (key != kEmptyKey) key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+        if (key != kEmptyKey) key = key_to_global(a.rows_map, key);
         uint64_t* dst = reinterpret_cast<uint64_t*>(a.xchg_peers[g] + kXchgKeysOff) +
                         (static_cast<size_t>(par) * a.xchg_world + a.xchg_rank) * a.xchg_slot_keys +
-                        static_cast<size_t>(b) * k + j;
+                        static_cast<size_t>(b) * ko + j;
         st_relaxed_sys_u64(dst, key);
       }
       continue;
     }
     int cnt = 0;
     const int bs = a.q_index ? a.q_index[b] : b;      // where this query's result belongs
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    for (int j = threadIdx.x; j < ko; j += blockDim.x) {
       uint64_t key = sorted[j];
       const bool valid = key != kEmptyKey;
       if (valid) {
-        key = (key & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(key_row(key) + a.row_base);
+        key = key_to_global(a.rows_map, key);
         cnt++;
       }
-      const size_t o = static_cast<size_t>(bs) * k + j;
+      const size_t o = static_cast<size_t>(bs) * ko + j;
       if (a.out_keys) a.out_keys[o] = key;
       if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
       if (a.out_dists) a.out_dists[o] = valid ? key_dist(key) : __int_as_float(0x7f800000);
@@ -538,6 +572,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     const int G = a.xchg_world;
     const size_t flag_idx = (static_cast<size_t>(par) * kXchgMaxGroups + blockIdx.y) * kXchgMaxWorld;
     __threadfence_system();
+    if (threadIdx.x == 0) s_flag = 0;                 // reused: 1 = a peer never delivered
     __syncthreads();
     if (static_cast<int>(threadIdx.x) < G) {
       uint32_t* theirs = reinterpret_cast<uint32_t*>(a.xchg_peers[threadIdx.x]) + flag_idx + a.xchg_rank;
@@ -547,6 +582,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       while (static_cast<int32_t>(ld_acquire_sys_u32(mine) - a.xchg_epoch) < 0) {
         if (global_timer_ns() - t0 > 20000000000ull) {    // 20 s: a peer never launched; flag it, do not hang the GPU
           atomicOr(reinterpret_cast<unsigned int*>(a.xchg_peers[a.xchg_rank] + kXchgStatusOff), 1u + threadIdx.x);
+          s_flag = 1;
           break;
         }
       }
@@ -558,11 +594,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     for (int qb = warp; qb < QB; qb += kScanWarps) {
       const int b = b0 + qb;
       if (b >= nB) break;
-      const uint64_t* lst = slots + static_cast<size_t>(lane < G ? lane : 0) * a.xchg_slot_keys + static_cast<size_t>(b) * k;
+      const uint64_t* lst = slots + static_cast<size_t>(lane < G ? lane : 0) * a.xchg_slot_keys + static_cast<size_t>(b) * ko;
       int pos = 0;
       uint64_t cur = (lane < G) ? ld_relaxed_sys_u64(lst) : kEmptyKey;
       int cnt = 0;
-      for (int r = 0; r < k; ++r) {
+      for (int r = 0; r < ko; ++r) {
         uint64_t m = cur;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
@@ -571,7 +607,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         }
         const bool valid = m != kEmptyKey;
         if (lane == 0) {
-          const size_t o = static_cast<size_t>(b) * k + r;
+          const size_t o = static_cast<size_t>(b) * ko + r;
           if (a.out_keys) a.out_keys[o] = m;
           if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(m)) : -1;
           if (a.out_dists) a.out_dists[o] = valid ? key_dist(m) : __int_as_float(0x7f800000);
@@ -580,11 +616,12 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
           cnt++;
           if (cur == m) {                        // global rows are unique: exactly one lane advances
             pos++;
-            cur = (pos < k) ? ld_relaxed_sys_u64(lst + pos) : kEmptyKey;
+            cur = (pos < ko) ? ld_relaxed_sys_u64(lst + pos) : kEmptyKey;
           }
         }
       }
-      if (lane == 0 && a.out_counts) a.out_counts[b] = cnt;
+      // a count of -1 tells the host that this result is built from a stale slot (a peer timed out)
+      if (lane == 0 && a.out_counts) a.out_counts[b] = s_flag ? -1 : cnt;
     }
   }
 }

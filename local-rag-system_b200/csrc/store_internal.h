@@ -1,0 +1,155 @@
+// Internal (not exported) view of one device store, shared by api.cu (the C ABI of a single store) and
+// sharded.cu (the single-process multi-device store built from several of them).
+#pragma once
+#include <pthread.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rag_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace rag {
+
+int fail(int code, const char* fmt, ...);      // sets the thread-local rag_last_error() text, returns code
+
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      (void)cudaGetLastError();                                                                   \
+      return ::rag::fail(_e == cudaErrorMemoryAllocation ? RAG_ENOMEM : RAG_ECUDA, "%s: %s (%s:%d)", \
+                         #expr, cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+    }                                                                                             \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// per-caller scratch: one stream + pinned staging + device scratch
+struct QueryCtx {
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  unsigned char* h_pin = nullptr;
+  size_t h_bytes = 0;
+  unsigned char* d_buf = nullptr;
+  size_t d_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;     // timed launches (synchronous API)
+  cudaEvent_t ev_done = nullptr;                 // marker a writer records on this context's stream (asynchronous readers)
+  bool launched = false;                         // ... since the last write waited for it
+  uint64_t seen_write = 0;                       // last write sequence this context's stream has been ordered behind
+  unsigned int* d_tickets = nullptr;             // kMaxTickets zeroed counters, self-resetting (scan kernel)
+  static constexpr int kMaxTickets = 4096;
+
+  int ensure_tickets();
+  int ensure_host(size_t bytes);
+  int ensure_dev(size_t bytes);
+  int ensure_events();
+  void destroy();
+};
+
+// small writes parked on the host until the next read (or until the buffer is full): the reference
+// adds one document per call (api/app.py:209-225) and upserts 1-5 chunks per call
+// (scripts/build_index.py:89-96); each would otherwise cost a host->device copy and a launch.
+struct PendingWrites {
+  static constexpr int64_t kMaxRows = 256;       // rows parked at most
+  static constexpr int64_t kSmallCall = 64;      // calls with more rows than this go straight to the device
+  unsigned char* h = nullptr;                    // pinned: [kMaxRows][dim] fp32 | [kMaxRows] int64 rows
+  int64_t n = 0;
+  std::unordered_map<int64_t, int64_t> slot_of;  // destination row -> slot (a second write to a row replaces the first)
+  cudaEvent_t ev_h2d = nullptr;                  // the previous flush has left the pinned block
+  bool in_flight = false;
+};
+
+struct SearchOut {
+  uint64_t* keys = nullptr;
+  int64_t* rows = nullptr;
+  float* dists = nullptr;
+  int32_t* counts = nullptr;
+};
+
+}  // namespace rag
+
+// peer-mapped buffers for the fused scan + all-gather + merge launch (multi-GPU)
+struct rag_exchange {
+  int device = 0, rank = 0, world = 1;
+  int64_t slot_keys = 0;
+  size_t bytes = 0;
+  unsigned char* d_local = nullptr;
+  std::vector<unsigned char*> peers;     // [world] base of every rank's buffer as mapped into this process
+  unsigned char** d_peers = nullptr;     // the same table on the device
+  uint32_t epoch = 0;
+  bool connected = false;
+  bool ipc = true;                       // peers were opened with cudaIpcOpenMemHandle (one process per GPU)
+  rag::QueryCtx host;                    // stream + pinned staging of the host-buffer call (rag_store_query_fused)
+};
+
+struct rag_store {
+  int dim = 0, dtype = 0, space = 0, device = 0;
+  int row_elems = 0;        // dim padded so that a row is a whole number of 16-byte chunks
+  size_t row_bytes = 0;
+  int exact_elems = 0;      // row pitch of the fp32 re-ranking plane (dim padded to 4), 0 = no plane
+  int sm_count = 0;
+  int64_t capacity = 0;     // rows allocated (multiple of 64)
+  int64_t rows = 0;         // high-water mark
+  int64_t live = 0;
+  void* d_vectors = nullptr;
+  float* d_exact = nullptr;               // bf16 stores: un-rounded fp32 rows (normalised for cosine) for the exact re-ranking
+  float* d_norms2 = nullptr;
+  float* d_max_norm2 = nullptr;           // [2] largest / smallest |stored row|^2 ever written
+  uint32_t* d_live = nullptr;
+  // fp32 stores, tensor regime: bf16 [capacity][hi(row_elems) | lo(row_elems)] split of the rows, built on
+  // the first large-batch query, kept in step by upsert, dropped (and rebuilt lazily) when the store grows
+  __nv_bfloat16* d_shadow = nullptr;
+  std::mutex shadow_mu;
+  uint32_t* d_masks[RAG_MAX_MASK_SLOTS] = {};     // each capacity / 32 words, zero beyond mask_words
+  int64_t mask_words[RAG_MAX_MASK_SLOTS] = {};
+  bool mask_set[RAG_MAX_MASK_SLOTS] = {};
+  std::vector<uint32_t> h_live;
+  std::vector<int64_t> free_rows;
+  // rows are placed by an outer layer (the single-process multi-device store): explicit rows may lie at or
+  // beyond the high-water mark and deleted rows are not remembered here (the outer layer re-uses them)
+  bool external_rows = false;
+  pthread_rwlock_t lock;
+  // scratch pool for the synchronous API
+  std::mutex pool_mu;
+  std::condition_variable pool_cv;
+  std::vector<rag::QueryCtx*> pool_free;
+  int pool_created = 0;
+  static constexpr int kMaxPool = 8;
+  // scratch for the asynchronous API, one per caller stream
+  std::mutex dev_mu;
+  std::unordered_map<void*, rag::QueryCtx*> dev_ctx;
+  rag::QueryCtx admin;      // upsert / delete / fetch / masks (used under the write lock)
+  cudaEvent_t ev_write = nullptr;         // recorded behind the last device-side write
+  std::atomic<uint64_t> write_seq{0};
+  rag::PendingWrites pending;
+  std::atomic<int64_t> pending_n{0};
+  std::atomic<int64_t> launches{0};
+  std::atomic<int> last_regime{0};
+  std::atomic<int> last_launches{0};
+  float last_kernel_ms = 0.0f;
+};
+
+namespace rag {
+
+// read lock held by the caller.  Orders the context's stream behind the last write, runs the regime's
+// kernels asynchronously on c->stream.  `scratch` must hold search_scratch_bytes().
+size_t search_scratch_bytes(const rag_store* s, int B, int k, int grid_x);
+int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
+                  int mask_slot, int regime, RowMap rows_map, const SearchOut& out, bool timed,
+                  rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor);
+int choose_regime(const rag_store* s, int B, int k, int flags);
+int batch_limit(const rag_store* s, int k);
+int check_query_args(const rag_store* s, int B, const void* q, int k, int mask_slot);
+// pending small writes -> device (takes the write lock itself when there is something to do)
+int flush_if_pending(rag_store* s);
+int dev_ctx_for(rag_store* s, void* stream, QueryCtx** out);
+// list length the scan keeps for a request of k hits (k + slack with the exact re-ranking)
+int scan_k(const rag_store* s, int k);
+
+}  // namespace rag

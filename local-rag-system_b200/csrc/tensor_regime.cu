@@ -62,7 +62,6 @@ template <int MODE> struct Ring {
   static constexpr int kStages = (MODE == 2) ? 14 : 7;      // 224 KB in flight per SM either way
 };
 constexpr int kRingBytes = 7 * kAtomsPerStage * kNB * kAtomK * 2;
-constexpr int kPrefetchTiles = 4;                      // L2 prefetch distance, in this CTA's tiles
 constexpr int kMmasPerStage = kStageK / 16;            // 16
 constexpr int kThreads = 224;            // TMA producer, MMA issuer A, 4 epilogue warps, MMA issuer B
 constexpr int kMmaWarpB = 6;
@@ -113,9 +112,6 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -697,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       }
       ++ti;
       const int row0 = static_cast<int>(t * kNB);
-      // pull this CTA's slice of a tile kPrefetchTiles steps ahead into L2 (hides DRAM latency
+      // optionally pull this CTA's slice of a tile a.prefetch steps ahead into L2 (hides DRAM latency
       // when the CTAs sharing a corpus tile have drifted apart and it is no longer L2-resident)
       {
         const int64_t tp = t + static_cast<int64_t>(a.prefetch) * a.cpm;
@@ -867,7 +863,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
   int n_mtiles, cpm, cl, mode;
-  size_t off_qbf16, off_qnorm, off_qf32, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
+  size_t off_qbf16, off_qnorm, off_qf32, off_qexact, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
 };
 
 // row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
@@ -886,6 +882,7 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.off_qbf16 = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * row_elems * 2);
   L.off_qnorm = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);
   L.off_qf32 = off;  off += align256(static_cast<size_t>(B) * row_elems * 4);
+  L.off_qexact = off; off += align256(static_cast<size_t>(B) * row_elems * 4);   // un-rounded queries (exact re-ranking)
   L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
   L.off_tau = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);      // directly behind `partial`: one memset
   L.off_prog = off; off += align256(static_cast<size_t>(L.cpm) * L.n_mtiles * 4);  // ... which also covers the pacing counters
@@ -937,42 +934,36 @@ cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int mode,
 
 }  // namespace
 
-struct Plan { int unused; };
-
 static bool split_enabled() {
   static const bool on = !(getenv("RAG_B200_F32_TENSOR") && atoi(getenv("RAG_B200_F32_TENSOR")) == 0);
   return on;
 }
 
-int candidates_kept(int dtype, int k) {
-  if (dtype == 1) return k;
+int candidates_kept(int dtype, int k, int rerank) {
+  if (dtype == 1 && !rerank) return k;
   return k <= 10 ? 16 : k + 16;      // slack for the exact re-ranking of approximately ranked rows
 }
 
-bool supported(int dtype, int row_elems, int k, int space) {
+bool supported(int dtype, int row_elems, int k, int space, int rerank) {
   (void)space;
   if (get_encode() == nullptr || k < 1) return false;
-  if (dtype == 1) return row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && k <= 1024;
+  if (dtype == 1) return row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && candidates_kept(dtype, k, rerank) <= 1024;
   // fp32 rows as [hi | lo] bf16: the A operand takes row_elems TMEM columns; k-steps must not straddle hi/lo
   return split_enabled() && row_elems >= 16 && row_elems % 16 == 0 && row_elems <= kMaxKCols &&
-         candidates_kept(dtype, k) <= 1024;
+         candidates_kept(dtype, k, 0) <= 1024;
 }
 
-size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count) {
-  if (!supported(dtype, row_elems, k, 0)) return 0;
+size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count, int rerank) {
+  if (!supported(dtype, row_elems, k, 0, rerank)) return 0;
   const int width = dtype == 1 ? row_elems : 2 * row_elems;
-  return make_layout(width, B, candidates_kept(dtype, k), sm_count).total;
+  return make_layout(width, B, candidates_kept(dtype, k, rerank), sm_count).total;
 }
 
-Plan* create_plan() { return new Plan(); }
-void destroy_plan(Plan* p) { delete p; }
-void invalidate(Plan*) {}
-
-cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* launches) {
-  if (!supported(p.dtype, p.row_elems, p.k, p.space)) return cudaErrorNotSupported;
+cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches) {
+  if (!supported(p.dtype, p.row_elems, p.k, p.space, p.rerank)) return cudaErrorNotSupported;
   const bool split = (p.dtype != 1);
   const int width = split ? 2 * p.row_elems : p.row_elems;       // bf16 elements per streamed row
-  const int kk = candidates_kept(p.dtype, p.k);
+  const int kk = candidates_kept(p.dtype, p.k, p.rerank);
   if (split && p.shadow == nullptr) return cudaErrorInvalidValue;
   const Layout L = make_layout(width, p.B, kk, p.sm_count);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(p.scratch + L.off_qbf16);
@@ -987,6 +978,8 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   pa.src = p.queries_raw; pa.B = p.B; pa.dim = p.dim; pa.row_elems = p.row_elems;
   pa.normalise = (p.space == 1); pa.round_bf16 = split ? 0 : 1; pa.split = split ? 1 : 0;
   pa.q_f32 = q_f32; pa.q_bf16 = q_bf16; pa.q_norm2 = q_norm;
+  float* q_exact = reinterpret_cast<float*>(p.scratch + L.off_qexact);
+  pa.q_exact = p.rerank ? q_exact : nullptr; pa.exact_elems = p.exact_elems;
   e = launch_prep_queries(pa, st);
   if (e != cudaSuccess) return e;
 
@@ -1055,6 +1048,7 @@ cudaError_t launch(Plan*, const Problem& p, cudaStream_t st, Result* out, int* l
   out->k_kept = kk;
   out->q_norm2 = q_norm;
   out->q_f32 = q_f32;
+  out->q_exact = q_exact;
   out->merged = reinterpret_cast<uint64_t*>(p.scratch + L.off_merged);
   if (launches) *launches += 2;
   return cudaSuccess;

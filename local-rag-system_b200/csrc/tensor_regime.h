@@ -15,8 +15,6 @@ constexpr int kStreamMaxBatch = 2;
 // split-precision contraction + exact re-ranking 0.35-0.40 ms for any B <= 16
 constexpr int kStreamMaxBatchF32 = 6;
 
-struct Plan;   // cached TMA descriptors etc. for one store
-
 struct Problem {
   const void* vectors;      // [n_rows][row_elems] bf16 (or fp32 when `shadow` is streamed instead), row-major
   const void* shadow;       // fp32 stores: [n_rows][hi(row_elems) | lo(row_elems)] bf16 split of the rows
@@ -28,30 +26,31 @@ struct Problem {
   const uint32_t* filter;
   int64_t filter_words;
   int dense;                // no filter and every row below n_rows is live
+  int rerank;               // bf16 store with an fp32 plane: keep k + slack candidates, also emit un-rounded queries
+  int exact_elems;          // row pitch of that plane (floats)
   const float* queries_raw; // [B][dim] fp32, unprepared
   int B, k;
   unsigned char* scratch;   // scratch_bytes() bytes
   int sm_count;
 };
 
-bool supported(int dtype, int row_elems, int k, int space);
+bool supported(int dtype, int row_elems, int k, int space, int rerank);
 // candidates the kernel keeps per query: k for bf16 stores (exact ranking of the stored values);
 // more for fp32 stores, whose rows are ranked through a bf16 hi/lo split and re-ranked exactly
-int candidates_kept(int dtype, int k);
-size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count);
-Plan* create_plan();
-void destroy_plan(Plan* p);
-void invalidate(Plan* p);     // corpus pointer / capacity changed
+// (and for bf16 stores that keep an un-rounded fp32 plane: ranked in bf16, re-ranked against the plane)
+int candidates_kept(int dtype, int k, int rerank);
+size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count, int rerank);
 struct Result {
   const uint64_t* partial;  // [S][B][k_kept] ascending candidate lists per query (inside `scratch`)
   int S;
   int k_kept;               // list length: k, or k + slack when ranking was approximate (fp32 stores)
   const float* q_norm2;     // [B] |prepared query|^2
   const float* q_f32;       // [B][row_elems] prepared queries (for the l2 refinement)
+  const float* q_exact;     // [B][exact_elems] normalised, un-rounded queries (Problem::rerank)
   uint64_t* merged;         // [B][k_kept] scratch for the merged keys before refinement
 };
 // Runs prep + contraction + fused select.
-cudaError_t launch(Plan* plan, const Problem& p, cudaStream_t st, Result* out, int* launches);
+cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches);
 
 }  // namespace tensor
 }  // namespace rag

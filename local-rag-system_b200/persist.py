@@ -34,6 +34,8 @@ class Journal:
         self._con = sqlite3.connect(db_path, check_same_thread=False)
         self._con.execute("PRAGMA journal_mode=WAL")
         self._con.execute("CREATE TABLE IF NOT EXISTS collections(name TEXT PRIMARY KEY, metadata TEXT)")
+        # names dropped with delete_collection(): never re-import them from a Chroma file lying in the same directory
+        self._con.execute("CREATE TABLE IF NOT EXISTS dropped(name TEXT PRIMARY KEY)")
         self._con.execute("CREATE TABLE IF NOT EXISTS wal(seq INTEGER PRIMARY KEY AUTOINCREMENT, collection TEXT, "
                           "op TEXT, id TEXT, vector BLOB, metadata TEXT, document TEXT)")
         self._con.commit()
@@ -44,6 +46,9 @@ class Journal:
             self._con.execute("INSERT OR IGNORE INTO collections(name, metadata) VALUES (?, ?)",
                               (self.collection, json.dumps(metadata) if metadata else None))
             self._con.commit()
+
+    def was_dropped(self) -> bool:
+        return self._con.execute("SELECT 1 FROM dropped WHERE name=?", (self.collection,)).fetchone() is not None
 
     def stored_metadata(self):
         row = self._con.execute("SELECT metadata FROM collections WHERE name=?", (self.collection,)).fetchone()
@@ -74,6 +79,7 @@ class Journal:
         with self._mu:
             self._con.execute("DELETE FROM wal WHERE collection=?", (self.collection,))
             self._con.execute("DELETE FROM collections WHERE name=?", (self.collection,))
+            self._con.execute("INSERT OR IGNORE INTO dropped(name) VALUES (?)", (self.collection,))
             self._con.commit()
         self.close()
 
@@ -155,6 +161,12 @@ def _replay(state, records):
         batch_op, ids, vecs, metas, docs = None, [], [], [], []
 
     for op, i, vec, md, doc in records:
+        if op == "update" and vec is None:
+            # Chroma logs metadata / document-only updates without a vector: they go through
+            # Collection.update (merge the keys, keep the stored vector), one at a time
+            flush()
+            col.update(ids=[i], metadatas=[md] if md else None, documents=[doc] if doc is not None else None)
+            continue
         op = "upsert" if op == "update" else op
         if op != batch_op or i in ids or len(ids) >= 4096:
             flush()
@@ -164,6 +176,10 @@ def _replay(state, records):
         metas.append(md)
         docs.append(doc)
     flush()
+
+
+# the keys that decide what the journal's vectors MEAN; a caller cannot change them for an existing collection
+_PINNED_KEYS = ("hnsw:space", "b200:dtype")
 
 
 def attach_journal(state, path: str):
@@ -182,9 +198,21 @@ def attach_journal(state, path: str):
         if known:
             if stored_md and not state.metadata:
                 state.apply_metadata(stored_md)
+            elif stored_md:
+                # the journal was written under the stored space / dtype: replaying it under another one would
+                # silently change every distance, so the stored values win (with a warning)
+                md = dict(state.metadata)
+                for key in _PINNED_KEYS:
+                    if key in stored_md and md.get(key, stored_md[key]) != stored_md[key]:
+                        logger.warning("collection %s exists with %s=%r; ignoring the requested %r", state.name, key,
+                                       stored_md[key], md.get(key))
+                    if key in stored_md:
+                        md[key] = stored_md[key]
+                state.apply_metadata(md)
             recs = list(journal.records())
     imported = False
-    if not known and os.path.exists(os.path.join(path, CHROMA_FILE)):
+    dropped = journal.was_dropped() if journal is not None else False
+    if not known and not dropped and os.path.exists(os.path.join(path, CHROMA_FILE)):
         try:
             md, recs = read_chroma_wal(path, state.name)
             if md and not state.metadata:
@@ -206,5 +234,5 @@ def _snapshot(state):
     rows = sorted(state.row_of.values())
     if not rows:
         return [], None, None, None
-    vec = state.store.fetch(np.array(rows, dtype=np.int64))
+    vec = state.store.fetch(np.array(rows, dtype=np.int64), exact=True)
     return ([state.ids[r] for r in rows], vec, [state.metas[r] for r in rows], [state.docs[r] for r in rows])

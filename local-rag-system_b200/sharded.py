@@ -161,10 +161,17 @@ class ShardedSearcher:
             if self.row_base:
                 rows = np.where(rows >= 0, rows + self.row_base, rows)
             return rows, dists, counts
-        q = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32))
-        if q.ndim == 1:
-            q = q[None, :]
-        B = q.shape[0]
+        qn = np.ascontiguousarray(queries, dtype=np.float32)
+        if qn.ndim == 1:
+            qn = qn[None, :]
+        B = qn.shape[0]
+        if self.exchange is not None and self.store.fused_ok(self.exchange, B, k, regime):
+            # ONE C call per rank: pinned staging, H2D, the fused scan + exchange + merge launch, D2H, wait
+            # (rag_store_query_fused).  No torch op, no Python between the copies and the launch.
+            self.last_path = "fused"
+            return self.store.query_fused_host(self.exchange, qn, k, mask_slot=mask_slot, row_base=self.row_base,
+                                               regime=regime)
+        q = torch.from_numpy(qn)
         b = self._buffers(B, k)
         b["q"].copy_(q if q.is_pinned() else q.pin_memory(), non_blocking=True)
         rows, dists, counts = self.search_device(b["q"], k, mask_slot, regime)

@@ -238,3 +238,62 @@ def evaluate_where_document(wd, docs, n_rows: int) -> np.ndarray:
             has = np.fromiter(((d is not None and cond in d) for d in docs[:n_rows]), dtype=bool, count=n_rows)
             out &= has if key == "$contains" else ~has
     return out
+
+
+# ---- one record at a time (incremental mask maintenance) -----------------------------------------
+def _same_kind(a, b) -> bool:
+    try:
+        return kind_of(a) == kind_of(b)
+    except ValueError:
+        return False
+
+
+def match_record(where, meta) -> bool:
+    """Does ONE record's metadata dict satisfy a validated `where`?  Same semantics as
+    MetadataColumns.evaluate (typed comparison; $ne / $nin also match records lacking the key); used to
+    patch the bits of the few rows a write touched instead of re-evaluating every row."""
+    if not where:
+        return True
+    meta = meta or {}
+    for key, cond in where.items():
+        if key == "$and":
+            if not all(match_record(w, meta) for w in cond):
+                return False
+        elif key == "$or":
+            if not any(match_record(w, meta) for w in cond):
+                return False
+        else:
+            have = meta.get(key)
+            ops = cond.items() if isinstance(cond, dict) else (("$eq", cond),)
+            for op, want in ops:
+                if op in ("$eq", "$ne"):
+                    hit = have is not None and _same_kind(have, want) and have == want
+                    ok = hit if op == "$eq" else not hit
+                elif op in ("$in", "$nin"):
+                    hit = have is not None and any(_same_kind(have, w) and have == w for w in want)
+                    ok = hit if op == "$in" else not hit
+                else:
+                    if have is None or not _same_kind(have, want):
+                        ok = False
+                    else:
+                        ok = {"$gt": have > want, "$gte": have >= want, "$lt": have < want, "$lte": have <= want}[op]
+                if not ok:
+                    return False
+    return True
+
+
+def match_document(wd, doc) -> bool:
+    if not wd:
+        return True
+    for key, cond in wd.items():
+        if key == "$and":
+            if not all(match_document(w, doc) for w in cond):
+                return False
+        elif key == "$or":
+            if not any(match_document(w, doc) for w in cond):
+                return False
+        else:
+            has = doc is not None and cond in doc
+            if has != (key == "$contains"):
+                return False
+    return True

@@ -287,8 +287,18 @@ class OracleCollection:
         for i, id_ in enumerate(ids):
             m = dict(metadatas[i]) if metadatas and metadatas[i] else None
             d = documents[i] if documents else None
-            if id_ in self.row_of:      # replace in place
+            if id_ in self.row_of:
+                # update in place.  Chroma's metadata segment handles an UPSERT record for an existing id
+                # with _update_metadata: the keys given are inserted-or-replaced, keys not given stay, and
+                # the document is just the key "chroma:document" -- so metadata MERGES and a call without
+                # documents keeps the old one [dep: chromadb 0.5.3 segment/impl/metadata/sqlite.py].  The
+                # shipped chroma.sqlite3 cannot tell merge from replace (its 12 re-upserts carry the same
+                # key set), which tests/test_oracle_golden.py states.
                 r = self.row_of[id_]
+                if self.metas[r]:
+                    m = {**self.metas[r], **(m or {})}
+                if not documents:
+                    d = self.docs[r]
                 self.vecs[r], self.metas[r], self.docs[r] = emb[i].copy(), m, d
             else:
                 self.row_of[id_] = len(self.ids)

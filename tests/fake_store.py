@@ -10,8 +10,9 @@ from oracle.exact_search import exact_search, prepare_corpus
 
 
 class FakeDeviceStore:
-    def __init__(self, dim, dtype="f32", space="l2", device=0, capacity_hint=0):
+    def __init__(self, dim, dtype="f32", space="l2", device=0, capacity_hint=0, rerank=None):
         self.dim, self.dtype, self.space, self.device = dim, dtype, space, device
+        self.rerank = False
         self.vec = np.zeros((0, dim), np.float32)
         self.live = np.zeros(0, bool)
         self.free = []
@@ -53,8 +54,19 @@ class FakeDeviceStore:
                 self.live[r] = False
                 self.free.append(r)
 
-    def fetch(self, rows):
+    def fetch(self, rows, exact=False):
         return self.vec[np.asarray(rows, np.int64)].copy()
+
+    def flush(self):
+        pass
+
+    def patch_mask(self, slot, rows, passing):
+        m = self.masks[slot]
+        rows = np.asarray(rows, np.int64).reshape(-1)
+        if rows.size and rows.max() >= m.shape[0]:
+            m = np.concatenate([m, np.zeros(int(rows.max()) + 1 - m.shape[0], bool)])
+        m[rows] = np.asarray(passing).astype(bool)
+        self.masks[slot] = m
 
     def set_mask(self, slot, passing):
         self.masks[slot] = np.asarray(passing, bool).copy()

@@ -5,6 +5,8 @@ tombstones.  Rank 0 prints MULTI_GPU_CHECK OK."""
 import os
 import sys
 
+os.environ.setdefault("RAG_B200_RERANK", "0")     # bit-identity of sharded vs single search is a property of the scan planes
+
 import numpy as np
 import torch
 import torch.distributed as dist

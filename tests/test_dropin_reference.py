@@ -36,11 +36,18 @@ def test_reference_test_suite_passes_unmodified_on_the_shim(tmp_path):
 
 
 def test_search_route_serves_the_shipped_index(tmp_path, golden):
-    """The unmodified FastAPI app, PERSIST_DIR = the reference's vector_store/:
+    """The unmodified FastAPI app, PERSIST_DIR = a copy of the reference's vector_store/:
     /health counts 25, /search returns the known answers with the reference's
     hit shape, the engine receives exactly the kwargs of api/app.py:544-549."""
+    # a private copy of the shipped index: the reference tree is read-only for this repo, and the journal
+    # (rag_b200.sqlite3) that PersistentClient creates next to chroma.sqlite3 must not outlive the test --
+    # otherwise later runs would find the collection "known" and never exercise the Chroma import again
+    import shutil
+    store = tmp_path / "vector_store"
+    shutil.copytree(os.path.join(REF, "vector_store"), store,
+                    ignore=shutil.ignore_patterns("rag_b200.sqlite3*"))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_search_script.py")], cwd=str(tmp_path),
-                       env=_env(tmp_path, os.path.join(REF, "vector_store")), capture_output=True, text=True,
+                       env=_env(tmp_path, str(store)), capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
@@ -60,3 +67,4 @@ def test_search_route_serves_the_shipped_index(tmp_path, golden):
     assert kw[1]["where"] == {"namespace": "history", "canonicality": "non"}
     assert out["chroma_add_ok"] is True and out["count_after_add"] == 26 and out["count_after_delete"] == 25
     assert out["chroma_add_bad"] is False
+    assert os.path.exists(store / "rag_b200.sqlite3")       # the import was carried into our own journal
