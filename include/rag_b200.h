@@ -267,6 +267,8 @@ RAG_API uint32_t rag_key_row(uint64_t key);
  * contraction kernel of the most recent rag_store_query on this thread's
  * store, and which regime it ran (1 = stream, 2 = tensor).                   */
 RAG_API int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches);
+/* device time (ms, CUDA events on the admin stream) of the upsert kernel of the last rag_store_upsert_dev */
+RAG_API float rag_store_last_upsert_ms(const rag_store* s);
 
 #ifdef __cplusplus
 }

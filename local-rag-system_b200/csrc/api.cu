@@ -290,19 +290,32 @@ int assign_rows(rag_store* s, int64_t n, const int64_t* rows, std::vector<int64_
   return RAG_OK;
 }
 
+bool contiguous(const int64_t* v, int64_t n) {
+  for (int64_t i = 1; i < n; ++i)
+    if (v[i] != v[0] + i) return false;
+  return true;
+}
+
 void mark_live(rag_store* s, const std::vector<int64_t>& dst) {
+  const int64_t n = (int64_t)dst.size();
+  if (n > 64 && dst[0] >= s->rows && contiguous(dst.data(), n)) {     // bulk append: whole bitmap words at a time
+    const int64_t lo = dst[0], hi = lo + n;
+    for (int64_t r = lo; r < hi;) {
+      const int64_t w = r >> 5, b = r & 31;
+      const int64_t take = std::min<int64_t>(32 - b, hi - r);
+      s->h_live[(size_t)w] |= (take == 32 ? 0xFFFFFFFFu : ((1u << take) - 1u) << b);
+      r += take;
+    }
+    s->live += n;
+    s->rows = hi;
+    return;
+  }
   for (int64_t r : dst) {
     if (r >= s->rows) s->rows = r + 1;
     uint32_t& w = s->h_live[(size_t)(r >> 5)];
     uint32_t bit = 1u << (r & 31);
     if (!(w & bit)) { w |= bit; s->live++; }
   }
-}
-
-bool contiguous(const int64_t* v, int64_t n) {
-  for (int64_t i = 1; i < n; ++i)
-    if (v[i] != v[0] + i) return false;
-  return true;
 }
 
 // launch the upsert kernel for fp32 vectors already on the device (write lock held, admin stream).
@@ -820,11 +833,15 @@ static int upsert_impl(rag_store* s, int64_t n, const float* vectors, bool on_de
       if (cudaMemcpyAsync(d_rows, dst.data(), (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c.stream) != cudaSuccess)
         return fail_cleanup(fail(RAG_ECUDA, "copy of the destination rows failed"));
     }
-    rc = launch_upsert_rows(s, vectors, n, d_rows, dst[0]);
+    rc = c.ensure_events();
+    if (rc == RAG_OK) (void)cudaEventRecord(c.ev0, c.stream);
+    if (rc == RAG_OK) rc = launch_upsert_rows(s, vectors, n, d_rows, dst[0]);
+    if (rc == RAG_OK) (void)cudaEventRecord(c.ev1, c.stream);
     // the caller's device buffer is only guaranteed to live until this call returns
     if (rc == RAG_OK) {
       cudaError_t e = cudaStreamSynchronize(c.stream);
       if (e != cudaSuccess) rc = fail(RAG_ECUDA, "upsert kernel failed: %s", cudaGetErrorString(e));
+      else if (cudaEventElapsedTime(&s->last_upsert_ms, c.ev0, c.ev1) != cudaSuccess) { (void)cudaGetLastError(); s->last_upsert_ms = 0.0f; }
     }
     if (rc != RAG_OK) return fail_cleanup(rc);
   } else {
@@ -1320,6 +1337,8 @@ int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* keys_dev
 uint64_t rag_key_pack(float dist, uint32_t row) { return make_key(dist, row); }
 float rag_key_dist(uint64_t key) { return key_dist(key); }
 uint32_t rag_key_row(uint64_t key) { return key_row(key); }
+
+float rag_store_last_upsert_ms(const rag_store* s) { return s ? s->last_upsert_ms : 0.0f; }
 
 int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");

@@ -133,6 +133,7 @@ struct rag_store {
   std::atomic<int> last_regime{0};
   std::atomic<int> last_launches{0};
   float last_kernel_ms = 0.0f;
+  float last_upsert_ms = 0.0f;            // device time of the last rag_store_upsert_dev kernel (CUDA events)
 };
 
 namespace rag {

@@ -101,6 +101,10 @@ class DeviceStore:
         N.check(self._lib.rag_store_upsert_dev(self._h, int(n), C.c_void_p(int(data_ptr)), _ptr(r), _ptr(out)))
         return out
 
+    def last_upsert_ms(self) -> float:
+        """Device time of the upsert kernel of the last upsert_device call (CUDA events)."""
+        return float(self._lib.rag_store_last_upsert_ms(self._h))
+
     def delete(self, rows):
         r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
         N.check(self._lib.rag_store_delete(self._h, r.shape[0], _ptr(r)))
