@@ -267,6 +267,10 @@ RAG_API uint32_t rag_key_row(uint64_t key);
  * contraction kernel of the most recent rag_store_query on this thread's
  * store, and which regime it ran (1 = stream, 2 = tensor).                   */
 RAG_API int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches);
+/* debugging aid: with RAG_B200_TENSOR_STATS=1 in the environment the tensor-regime epilogue counts, on the
+ * CURRENT device, [0] tiles drained per warp, [1] / [2] tiles passing the first / second reject test,
+ * [3] candidate scores examined, [4] list insertions, [5] quantile-list updates; out8 receives 8 counters */
+RAG_API int rag_debug_tensor_stats(uint64_t* out8, int reset);
 /* device time (ms, CUDA events on the admin stream) of the upsert kernel of the last rag_store_upsert_dev */
 RAG_API float rag_store_last_upsert_ms(const rag_store* s);
 

@@ -92,6 +92,7 @@ SIGNATURES = {
     "rag_key_pack": (C.c_uint64, [C.c_float, C.c_uint32]),
     "rag_key_dist": (C.c_float, [C.c_uint64]),
     "rag_key_row": (C.c_uint32, [C.c_uint64]),
+    "rag_debug_tensor_stats": (C.c_int, [_u64p, C.c_int]),
     "rag_store_last_upsert_ms": (C.c_float, [_p]),
     "rag_store_last_query_info": (C.c_int, [_p, _f32p, _i32p, _i32p]),
 }

@@ -182,7 +182,7 @@ int grow(rag_store* s, int64_t need) {
   if (need <= s->capacity) return RAG_OK;
   if (need > 0xFFFFFFF0ll) return fail(RAG_EINVAL, "a store holds at most 2^32-16 rows");
   int64_t cap = std::max<int64_t>(need, std::max<int64_t>(1024, s->capacity * 2));
-  cap = (cap + 63) / 64 * 64;          // whole 64-row tiles: the tensor regime reads live words 2t and 2t + 1
+  cap = (cap + 127) / 128 * 128;       // whole 128-row tiles: the tensor regime reads all the live words of a tile
   void* nv = nullptr;
   float* nn = nullptr;
   float* nx = nullptr;
@@ -200,7 +200,7 @@ int grow(rag_store* s, int64_t need) {
   };
   cudaError_t e = alloc_rows(cap);
   if (e != cudaSuccess && cap > need) {   // doubling did not fit: take exactly what is needed
-    cap = (need + 63) / 64 * 64;
+    cap = (need + 127) / 128 * 128;
     e = alloc_rows(cap);
   }
   if (e != cudaSuccess) return fail(RAG_ENOMEM, "cudaMalloc of %zu bytes for the corpus failed: %s", (size_t)cap * per_row, cudaGetErrorString(e));
@@ -424,6 +424,34 @@ ScratchLayout scratch_layout(const rag_store* s, int B, int k, int grid_x) {
 
 }  // namespace
 
+static bool fused_merge_enabled() {
+  static const bool on = !(getenv("RAG_B200_FUSED_MERGE") && atoi(getenv("RAG_B200_FUSED_MERGE")) == 0);
+  return on;
+}
+
+bool rag::direct_host_ok(const rag_store* s, int B, int k, int regime) {
+  static const bool on = !(getenv("RAG_B200_DIRECT_HOST") && atoi(getenv("RAG_B200_DIRECT_HOST")) == 0);
+  return on && regime == 1 && fused_merge_enabled() && (int64_t)B * k <= 4096 &&
+         scan_stream_groups(B, s->dtype, s->row_elems, scan_k(s, k)) == 1;
+}
+
+int rag::wait_host_flag(const volatile uint32_t* flag, uint32_t seq, cudaStream_t st) {
+  for (uint32_t spins = 1;; ++spins) {
+    if (*flag == seq) { std::atomic_thread_fence(std::memory_order_acquire); return RAG_OK; }
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0x3FFFu) == 0) {          // now and then: has the stream died, or finished without the signal?
+      const cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {
+        if (*flag == seq) { std::atomic_thread_fence(std::memory_order_acquire); return RAG_OK; }
+        return fail(RAG_ECUDA, "the search finished without raising its completion signal");
+      }
+      if (e != cudaErrorNotReady) { (void)cudaGetLastError(); return fail(RAG_ECUDA, "search failed: %s", cudaGetErrorString(e)); }
+    }
+  }
+}
+
 int rag::scan_k(const rag_store* s, int k) {
   if (!s->exact_elems) return k;
   return k <= 10 ? 16 : k + 16;        // slack for the exact re-ranking (same rule as tensor::candidates_kept)
@@ -523,7 +551,7 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
     d_merged = tres.merged;
     if (timed) CUDA_TRY(cudaEventRecord(c->ev1, st));
   } else {
-    static const bool fused = !(getenv("RAG_B200_FUSED_MERGE") && atoi(getenv("RAG_B200_FUSED_MERGE")) == 0);
+    const bool fused = fused_merge_enabled();
     if (B > QueryCtx::kMaxTickets) return fail(RAG_EINVAL, "batch %d exceeds %d", B, QueryCtx::kMaxTickets);
     sa.k = ks; sa.k_out = k;
     sa.partial = d_partial;
@@ -534,6 +562,10 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
       sa.done = c->d_tickets;
       sa.queries = nullptr; sa.queries_raw = d_queries_raw;
       if (rerank) { sa.exact = s->d_exact; sa.exact_elems = s->exact_elems; }
+      if (out.done_flag != nullptr && direct_host_ok(s, B, k, 1)) {
+        sa.done_flag = out.done_flag; sa.done_seq = out.done_seq;
+        if (out.armed) *out.armed = true;
+      }
     } else {          // unfused debugging mode: separate prep, merge and re-ranking kernels
       PrepArgs pa{};
       pa.src = d_queries_raw; pa.B = B; pa.dim = s->dim; pa.row_elems = s->row_elems;
@@ -1077,7 +1109,7 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
     const size_t dist_b = align_up((size_t)Bc * k * sizeof(float), 256);
     const size_t cnt_b = align_up((size_t)Bc * sizeof(int32_t), 256);
     const size_t scr_b = search_scratch_bytes(s, Bc, k, grid_x);
-    rc = c->ensure_host(in_b + rows_b + dist_b + cnt_b);
+    rc = c->ensure_host(in_b + rows_b + dist_b + cnt_b + 256);      // + the completion flag
     if (rc != RAG_OK) return rc;
     rc = c->ensure_dev(in_b + rows_b + dist_b + cnt_b + scr_b);
     if (rc != RAG_OK) return rc;
@@ -1091,17 +1123,41 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
 
     memcpy(c->h_pin, queries + (size_t)b0 * s->dim, (size_t)Bc * s->dim * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(d_in, c->h_pin, (size_t)Bc * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    bool armed = false;
+    if (direct_host_ok(s, Bc, k, regime)) {
+      // small stream-regime batch: the kernel writes the result straight into the pinned block (mapped host
+      // memory) and raises a flag there -- no device-to-host copy, no stream synchronisation
+      so.rows = reinterpret_cast<int64_t*>(c->h_pin + in_b);
+      so.dists = reinterpret_cast<float*>(c->h_pin + in_b + rows_b);
+      so.counts = reinterpret_cast<int32_t*>(c->h_pin + in_b + rows_b + dist_b);
+      so.done_flag = reinterpret_cast<uint32_t*>(c->h_pin + in_b + rows_b + dist_b + cnt_b);
+      so.done_seq = ++c->signal_seq ? c->signal_seq : ++c->signal_seq;
+      so.armed = &armed;
+    }
     rc = search_device(s, c, scratch, Bc, d_in, k, mask_slot, regime, RowMap{}, so, true, nullptr, 0u, flags == RAG_QUERY_FORCE_TENSOR);
     if (rc != RAG_OK) return rc;
     regime_used = s->last_regime.load();     // the regime that actually ran (an fp32 store may have fallen back)
-    // one D2H for rows + dists + counts (contiguous in the scratch and in the pinned buffer)
-    CUDA_TRY(cudaMemcpyAsync(c->h_pin + in_b, d + in_b, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (armed) {
+      rc = wait_host_flag(so.done_flag, so.done_seq, c->stream);
+      if (rc != RAG_OK) return rc;
+    } else {
+      // one D2H for rows + dists + counts (contiguous in the scratch and in the pinned buffer)
+      CUDA_TRY(cudaMemcpyAsync(c->h_pin + in_b, d + in_b, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     memcpy(out_rows + (size_t)b0 * k, c->h_pin + in_b, (size_t)Bc * k * sizeof(int64_t));
     memcpy(out_dists + (size_t)b0 * k, c->h_pin + in_b + rows_b, (size_t)Bc * k * sizeof(float));
     memcpy(out_counts + b0, c->h_pin + in_b + rows_b + dist_b, (size_t)Bc * sizeof(int32_t));
     float ms = 0.0f;
-    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) total_ms += ms;
+    if (armed) {
+      // the flag is raised a moment before the kernel (and the event behind it) completes: leave the timing to
+      // rag_store_last_query_info(), which waits for the event only if somebody asks
+      s->timing_ctx.store(c, std::memory_order_release);
+    } else if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) {
+      total_ms += ms;
+    } else {
+      (void)cudaGetLastError();
+    }
     total_launches += s->last_launches.load();
   }
   s->last_kernel_ms = total_ms;
@@ -1295,7 +1351,7 @@ int rag_store_query_fused(rag_store* s, rag_exchange* x, int B, const float* que
   const size_t dist_b = align_up((size_t)B * k * sizeof(float), 256);
   const size_t cnt_b = align_up((size_t)B * sizeof(int32_t), 256);
   const size_t io_b = in_b + rows_b + dist_b + cnt_b;
-  rc = c->ensure_host(io_b);
+  rc = c->ensure_host(io_b + 256);         // + the completion flag
   if (rc != RAG_OK) return rc;
   const int grid_x = scan_stream_grid_x(s->sm_count, s->rows);
   rc = c->ensure_dev(io_b + search_scratch_bytes(s, B, k, grid_x));
@@ -1307,11 +1363,25 @@ int rag_store_query_fused(rag_store* s, rag_exchange* x, int B, const float* que
   so.rows = reinterpret_cast<int64_t*>(d + in_b);
   so.dists = reinterpret_cast<float*>(d + in_b + rows_b);
   so.counts = reinterpret_cast<int32_t*>(d + in_b + rows_b + dist_b);
+  bool armed = false;
+  if (direct_host_ok(s, B, k, 1)) {       // result + completion flag straight into the pinned block (see rag_store_query)
+    so.rows = reinterpret_cast<int64_t*>(c->h_pin + in_b);
+    so.dists = reinterpret_cast<float*>(c->h_pin + in_b + rows_b);
+    so.counts = reinterpret_cast<int32_t*>(c->h_pin + in_b + rows_b + dist_b);
+    so.done_flag = reinterpret_cast<uint32_t*>(c->h_pin + io_b);
+    so.done_seq = ++c->signal_seq ? c->signal_seq : ++c->signal_seq;
+    so.armed = &armed;
+  }
   rc = search_device(s, c, d + io_b, B, reinterpret_cast<const float*>(d), k, mask_slot, 1, RowMap{row_base, 0u, 1u}, so,
                      false, x, epoch, false);
   if (rc != RAG_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(c->h_pin + in_b, d + in_b, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (armed) {
+    rc = wait_host_flag(so.done_flag, so.done_seq, c->stream);
+    if (rc != RAG_OK) return rc;
+  } else {
+    CUDA_TRY(cudaMemcpyAsync(c->h_pin + in_b, d + in_b, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
   memcpy(out_rows, c->h_pin + in_b, (size_t)B * k * sizeof(int64_t));
   memcpy(out_dists, c->h_pin + in_b + rows_b, (size_t)B * k * sizeof(float));
   memcpy(out_counts, c->h_pin + in_b + rows_b + dist_b, (size_t)B * sizeof(int32_t));
@@ -1338,10 +1408,22 @@ uint64_t rag_key_pack(float dist, uint32_t row) { return make_key(dist, row); }
 float rag_key_dist(uint64_t key) { return key_dist(key); }
 uint32_t rag_key_row(uint64_t key) { return key_row(key); }
 
+int rag_debug_tensor_stats(uint64_t* out8, int reset) {
+  static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "counter width");
+  return tensor::read_stats(reinterpret_cast<unsigned long long*>(out8), reset) == 0 ? RAG_OK : fail(RAG_ECUDA, "reading the counters failed");
+}
+
 float rag_store_last_upsert_ms(const rag_store* s) { return s ? s->last_upsert_ms : 0.0f; }
 
 int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");
+  rag_store* ms_ = const_cast<rag_store*>(s);
+  if (QueryCtx* c = ms_->timing_ctx.exchange(nullptr, std::memory_order_acq_rel)) {
+    float ms = 0.0f;      // contexts live as long as the store; a concurrent query on the same context only blurs the number
+    if (cudaSetDevice(s->device) == cudaSuccess && cudaEventSynchronize(c->ev1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) ms_->last_kernel_ms = ms;
+    else (void)cudaGetLastError();
+  }
   if (kernel_ms) *kernel_ms = s->last_kernel_ms;
   if (regime) *regime = s->last_regime.load();
   if (launches) *launches = s->last_launches.load();

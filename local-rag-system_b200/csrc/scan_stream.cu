@@ -560,7 +560,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       if (threadIdx.x == 0) a.out_counts[bs] = s_total;
     }
   }
-  if (a.xchg_peers == nullptr) return;
+  if (a.xchg_peers == nullptr) {
+    if (a.done_flag != nullptr) {         // results went to host memory: make them visible, then raise the flag
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_sys_u32(a.done_flag, a.done_seq);
+    }
+    return;
+  }
 
   // ---- fused all-gather + cross-shard merge over peer memory ----------------------------------
   // Every thread's stores above are made visible system-wide before ONE flag per peer is raised;
@@ -622,6 +629,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       }
       // a count of -1 tells the host that this result is built from a stale slot (a peer timed out)
       if (lane == 0 && a.out_counts) a.out_counts[b] = s_flag ? -1 : cnt;
+    }
+    if (a.done_flag != nullptr) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_sys_u32(a.done_flag, a.done_seq);
     }
   }
 }

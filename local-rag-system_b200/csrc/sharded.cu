@@ -78,6 +78,7 @@ struct rag_sharded {
   std::vector<std::string> job_err;
   // introspection
   float last_kernel_ms = 0.0f;
+  bool timing_pending = false;
   int last_regime = 0, last_launches = 0, last_path = 0;
 };
 
@@ -497,8 +498,11 @@ int rag_sharded_query(rag_sharded* s, int B, const float* queries, int k, int ma
     const size_t cnt_b = align_up((size_t)Bc * sizeof(int32_t), 256);
     QueryCtx* c0 = &s->ctx[0];
     CUDA_TRY(cudaSetDevice(s->device[0]));
-    rc = c0->ensure_host(rows_b + dist_b + cnt_b);
+    rc = c0->ensure_host(rows_b + dist_b + cnt_b + 256);      // + the completion flag
     if (rc != RAG_OK) return rc;
+    bool armed = false;
+    uint32_t* done_flag = reinterpret_cast<uint32_t*>(c0->h_pin + rows_b + dist_b + cnt_b);
+    uint32_t done_seq = 0;
 
     bool fused = s->fused_ok && regime == 1;
     if (fused)
@@ -520,6 +524,12 @@ int rag_sharded_query(rag_sharded* s, int B, const float* queries, int k, int ma
       SearchOut so{};
       if (rc == RAG_OK) {
         d_out = c0->d_buf + in_b;
+        if (direct_host_ok(s0, Bc, k, 1)) {
+          // device 0 writes the merged result straight into the pinned block and raises a flag there
+          d_out = c0->h_pin;
+          done_seq = ++c0->signal_seq ? c0->signal_seq : ++c0->signal_seq;
+          so.done_flag = done_flag; so.done_seq = done_seq; so.armed = &armed;
+        }
         so.rows = reinterpret_cast<int64_t*>(d_out);
         so.dists = reinterpret_cast<float*>(d_out + rows_b);
         so.counts = reinterpret_cast<int32_t*>(d_out + rows_b + dist_b);
@@ -588,15 +598,21 @@ int rag_sharded_query(rag_sharded* s, int B, const float* queries, int k, int ma
       total_launches += 1;
     }
     CUDA_TRY(cudaSetDevice(s->device[0]));
-    CUDA_TRY(cudaMemcpyAsync(c0->h_pin, d_out, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c0->stream));
-    CUDA_TRY(cudaStreamSynchronize(c0->stream));
+    if (armed) {
+      rc = wait_host_flag(done_flag, done_seq, c0->stream);
+      if (rc != RAG_OK) return rc;
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(c0->h_pin, d_out, rows_b + dist_b + cnt_b, cudaMemcpyDeviceToHost, c0->stream));
+      CUDA_TRY(cudaStreamSynchronize(c0->stream));
+    }
     memcpy(out_rows + (size_t)b0 * k, c0->h_pin, (size_t)Bc * k * sizeof(int64_t));
     memcpy(out_dists + (size_t)b0 * k, c0->h_pin + rows_b, (size_t)Bc * k * sizeof(float));
     memcpy(out_counts + b0, c0->h_pin + rows_b + dist_b, (size_t)Bc * sizeof(int32_t));
     for (int b = 0; b < Bc; ++b)
       if (out_counts[b0 + b] < 0) return fail(RAG_ECUDA, "fused exchange: a shard did not deliver its candidates within 20 s");
     float ms = 0.0f;
-    if (c0->ev0 && c0->ev1 && cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) total_ms += ms;
+    if (armed) s->timing_pending = true;              // read lazily by rag_sharded_last_query_info
+    else if (c0->ev0 && c0->ev1 && cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) total_ms += ms;
     else (void)cudaGetLastError();
     s->last_regime = s0->last_regime.load();
   }
@@ -607,6 +623,15 @@ int rag_sharded_query(rag_sharded* s, int B, const float* queries, int k, int ma
 
 int rag_sharded_last_query_info(const rag_sharded* s, float* kernel_ms, int* regime, int* launches, int* path) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");
+  if (s->timing_pending) {
+    rag_sharded* m = const_cast<rag_sharded*>(s);
+    QueryCtx* c0 = &m->ctx[0];
+    float ms = 0.0f;
+    m->timing_pending = false;
+    if (cudaSetDevice(s->device[0]) == cudaSuccess && c0->ev1 && cudaEventSynchronize(c0->ev1) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, c0->ev0, c0->ev1) == cudaSuccess) m->last_kernel_ms = ms;
+    else (void)cudaGetLastError();
+  }
   if (kernel_ms) *kernel_ms = s->last_kernel_ms;
   if (regime) *regime = s->last_regime;
   if (launches) *launches = s->last_launches;

@@ -42,6 +42,7 @@ struct QueryCtx {
   cudaEvent_t ev_done = nullptr;                 // marker a writer records on this context's stream (asynchronous readers)
   bool launched = false;                         // ... since the last write waited for it
   uint64_t seen_write = 0;                       // last write sequence this context's stream has been ordered behind
+  uint32_t signal_seq = 0;                       // last value handed to a kernel as its completion signal
   unsigned int* d_tickets = nullptr;             // kMaxTickets zeroed counters, self-resetting (scan kernel)
   static constexpr int kMaxTickets = 4096;
 
@@ -70,6 +71,12 @@ struct SearchOut {
   int64_t* rows = nullptr;
   float* dists = nullptr;
   int32_t* counts = nullptr;
+  // optional completion flag in mapped pinned host memory (rows / dists / counts then point there too): if the
+  // launch can raise it (fused stream regime, one query group) search_device sets *armed and the caller polls
+  // the flag with wait_host_flag() instead of copying the result back and synchronising the stream
+  uint32_t* done_flag = nullptr;
+  uint32_t done_seq = 0;
+  bool* armed = nullptr;
 };
 
 }  // namespace rag
@@ -94,7 +101,7 @@ struct rag_store {
   size_t row_bytes = 0;
   int exact_elems = 0;      // row pitch of the fp32 re-ranking plane (dim padded to 4), 0 = no plane
   int sm_count = 0;
-  int64_t capacity = 0;     // rows allocated (multiple of 64)
+  int64_t capacity = 0;     // rows allocated (multiple of 128)
   int64_t rows = 0;         // high-water mark
   int64_t live = 0;
   void* d_vectors = nullptr;
@@ -133,6 +140,7 @@ struct rag_store {
   std::atomic<int> last_regime{0};
   std::atomic<int> last_launches{0};
   float last_kernel_ms = 0.0f;
+  std::atomic<rag::QueryCtx*> timing_ctx{nullptr};   // events of the last flag-signalled query, read lazily
   float last_upsert_ms = 0.0f;            // device time of the last rag_store_upsert_dev kernel (CUDA events)
 };
 
@@ -147,6 +155,10 @@ int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, cons
 int choose_regime(const rag_store* s, int B, int k, int flags);
 int batch_limit(const rag_store* s, int k);
 int check_query_args(const rag_store* s, int B, const void* q, int k, int mask_slot);
+// can a (B, k) search of this store write its result straight to host memory and raise a flag?
+bool direct_host_ok(const rag_store* s, int B, int k, int regime);
+// spin on a completion flag in mapped pinned memory; falls back to the stream's status to surface errors
+int wait_host_flag(const volatile uint32_t* flag, uint32_t seq, cudaStream_t st);
 // pending small writes -> device (takes the write lock itself when there is something to do)
 int flush_if_pending(rag_store* s);
 int dev_ctx_for(rag_store* s, void* stream, QueryCtx** out);

@@ -47,7 +47,8 @@ namespace tensor {
 namespace {
 
 constexpr int kM = 128;              // queries per CTA (MMA M)
-constexpr int kNB = 64;              // corpus rows per tile (MMA N)
+constexpr int kNB = 64;              // corpus rows per tile (MMA N); kNBWide where tensor memory has room (see below)
+constexpr int kNBWide = 128;
 constexpr int kAtomK = 64;           // bf16 elements per 128-byte swizzle atom row
 constexpr int kAtomsPerStage = 4;
 constexpr int kStageK = kAtomK * kAtomsPerStage;      // 256 K elements per pipeline stage
@@ -55,11 +56,15 @@ constexpr int kStageK = kAtomK * kAtomsPerStage;      // 256 K elements per pipe
 // a tile (4 atoms x 8 KB = 32 KB, 7 stages).  MODE 2 (cta_group::2 pair): each CTA of the pair holds
 // only ITS 32 rows of every tile (4 atoms x 4 KB = 16 KB, 14 stages); the pair's tensor cores share
 // the two halves, which halves the shared-memory traffic per SM.
-template <int MODE> struct Ring {
-  static constexpr int kRows = (MODE == 2) ? kNB / 2 : kNB;
+// NB = 128 (pairs only, A operand <= 256 columns, i.e. D <= 512): every per-tile and per-instruction cost -- the
+// issuing thread's ~13 scalar instructions per MMA, barrier hand-offs, the epilogue's fixed part -- is paid per
+// 128 rows instead of 64.  At D = 384 a 64-row tile is only 768 cycles of tensor work, LESS than what the two
+// issuing threads and the epilogue warps need per tile; the wide tile doubles the budget.
+template <int MODE, int NB = kNB> struct Ring {
+  static constexpr int kRows = (MODE == 2) ? NB / 2 : NB;
   static constexpr int kAtomBytes = kRows * kAtomK * 2;
   static constexpr int kStageBytes = kAtomsPerStage * kAtomBytes;
-  static constexpr int kStages = (MODE == 2) ? 14 : 7;      // 224 KB in flight per SM either way
+  static constexpr int kStages = (7 * kAtomsPerStage * kNB * kAtomK * 2) / kStageBytes;      // 224 KB in flight per SM either way
 };
 constexpr int kRingBytes = 7 * kAtomsPerStage * kNB * kAtomK * 2;
 constexpr int kMmasPerStage = kStageK / 16;            // 16
@@ -69,7 +74,6 @@ constexpr int kEpiWarp0 = 2;
 constexpr int kTmemCols = 512;
 constexpr int kMaxKCols = 384;       // A operand: up to 768 bf16 per query
 constexpr int kMaxAccBufs = 4;
-constexpr int kAccCols = kNB;        // fp32 accumulator columns per buffer
 constexpr int kSmemBytes = kRingBytes + 1024 /*align*/ + 512 /*barriers*/;
 
 // ---- PTX wrappers -------------------------------------------------------------
@@ -243,13 +247,18 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
   return d;
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = kNB
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kNB >> 3) << 17) |
-                            (static_cast<uint32_t>(kM >> 4) << 24);
-// the pair's instruction: M = 256 (128 rows in each CTA's tensor memory)
-constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kNB >> 3) << 17) |
-                                (static_cast<uint32_t>((2 * kM) >> 4) << 24);
+constexpr uint32_t make_idesc(int n, int m) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+// the pair's instruction has M = 256 (128 rows in each CTA's tensor memory)
+
+// selection statistics of the epilogue (RAG_B200_TENSOR_STATS=1; read with rag_debug_tensor_stats):
+// [0] tiles drained per epilogue warp, [1] tiles that passed the first reject test, [2] ... the second (l2),
+// [3] candidate scores examined, [4] list insertions, [5] quantile-list updates
+__device__ unsigned long long g_tensor_stats[8];
 
 struct Args {
+  int stats;                     // 1: count into g_tensor_stats (debug; costs a few atomics per slow-path tile)
   const __nv_bfloat16* q_bf16;   // [n_mtiles*128][row_elems] prepared queries, zero rows beyond B
   const float* q_norm2;          // [n_mtiles*128]
   const float* x_norm2;          // [n_rows] (l2)
@@ -367,13 +376,17 @@ struct TopList {
 // for both (each tensor core contracts its own 128 queries with the 64 rows held by the pair), so a
 // corpus byte is written to and read from shared memory once per PAIR -- half the per-SM traffic of
 // the multicast scheme (which at 64 B/clk in + 64 B/clk out sat at the SM's shared-memory limit).
-template <int KL, bool L2, int MODE>
+template <int KL, bool L2, int MODE, int NB>
 __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
   constexpr int CL = (MODE == 0) ? 1 : 2;
   constexpr bool PAIR = (MODE == 2);
-  constexpr int kStages = Ring<MODE>::kStages;
-  constexpr int kStageBytes = Ring<MODE>::kStageBytes;
-  constexpr int kAtomBytes = Ring<MODE>::kAtomBytes;
+  constexpr int kStages = Ring<MODE, NB>::kStages;
+  constexpr int kStageBytes = Ring<MODE, NB>::kStageBytes;
+  constexpr int kAtomBytes = Ring<MODE, NB>::kAtomBytes;
+  constexpr int kAccCols = NB;                              // fp32 accumulator columns per buffer
+  constexpr int NW = NB / 32;                               // bitmap words per tile
+  constexpr int NSUB = NB / 64;                             // 64-column halves the epilogue drains one after the other
+  static_assert(NB == 64 || (NB == 128 && MODE == 2), "the wide tile exists for CTA pairs only");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;             // 1024-byte aligned stage ring
@@ -396,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   // clusters of CL CTAs lie along x (a cta_group::2 pair must): x = cj * CL + rank, y = group of CL query tiles
   const int mt = static_cast<int>(blockIdx.y) * CL + static_cast<int>(blockIdx.x % CL);   // query tile
   const int cj = static_cast<int>(blockIdx.x / CL);   // position among the CTAs of this query tile
-  const int64_t n_tiles = (a.n_rows + kNB - 1) / kNB;
+  const int64_t n_tiles = (a.n_rows + NB - 1) / NB;
   const int kcols = ((a.row_elems + 15) / 16) * 8;         // TMEM columns of the A operand
   const int k_steps = (a.row_elems + 15) / 16;             // MMAs per tile
   const int n_stages_per_tile = (a.row_elems + kStageK - 1) / kStageK;
@@ -404,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), PAIR ? 1 : CL); }   // (unused ones included)
-    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), PAIR ? 8 : 4); }
+    for (int b = 0; b < kMaxAccBufs; ++b) { mbar_init(accf_bar(b), 1); mbar_init(acce_bar(b), PAIR ? 8 : 4); }   // one arrival per epilogue warp
     mbar_init(aready_bar, 8);
     fence_barrier_init();
   }
@@ -433,33 +446,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   struct TileWalker {
     const Args& a;
     int64_t t, n_tiles;
-    uint32_t p0, p1;      // prefetched mask words of tile t
+    uint32_t p[NW];       // prefetched mask words of tile t
     bool masks;           // false: the caller only needs the tile sequence (dense stores: nothing to compute)
     __device__ __forceinline__ void fetch() {
-      if (t >= n_tiles) { p0 = p1 = 0u; return; }
-      if (a.dense && !masks) { p0 = 1u; p1 = 0u; return; }
-      if (a.dense) {
-        const int64_t left = a.n_rows - t * kNB;
-        if (left >= kNB) { p0 = p1 = 0xffffffffu; return; }
-        p0 = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-        p1 = left >= 64 ? 0xffffffffu : (left > 32 ? ((1u << (left - 32)) - 1u) : 0u);
+      if (t >= n_tiles) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) p[i] = 0u;
         return;
       }
-      p0 = __ldg(a.live + 2 * t);
-      p1 = __ldg(a.live + 2 * t + 1);
-      if (a.filter != nullptr) {
-        p0 &= (2 * t < a.filter_words) ? __ldg(a.filter + 2 * t) : 0u;
-        p1 &= (2 * t + 1 < a.filter_words) ? __ldg(a.filter + 2 * t + 1) : 0u;
+      if (a.dense && !masks) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) p[i] = (i == 0) ? 1u : 0u;
+        return;
+      }
+      if (a.dense) {
+        const int64_t left = a.n_rows - t * NB;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const int64_t li = left - 32 * i;
+          p[i] = li >= 32 ? 0xffffffffu : (li > 0 ? ((1u << li) - 1u) : 0u);
+        }
+        return;
+      }
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const int64_t w = static_cast<int64_t>(NW) * t + i;
+        p[i] = __ldg(a.live + w);
+        if (a.filter != nullptr) p[i] &= (w < a.filter_words) ? __ldg(a.filter + w) : 0u;
       }
     }
     __device__ __forceinline__ TileWalker(const Args& a_, int64_t t0, int64_t n, bool masks_ = true)
         : a(a_), t(t0), n_tiles(n), masks(masks_) { fetch(); }
-    __device__ __forceinline__ bool next(int64_t& tile, uint32_t& w0, uint32_t& w1) {
+    __device__ __forceinline__ bool next(int64_t& tile, uint32_t* w) {
       while (t < n_tiles) {
-        tile = t; w0 = p0; w1 = p1;
+        tile = t;
+        uint32_t any = 0u;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) { w[i] = p[i]; any |= p[i]; }
         t += a.cpm;
         fetch();
-        if ((w0 | w1) != 0u) return true;
+        if (any != 0u) return true;
       }
       return false;
     }
@@ -512,8 +538,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     uint32_t it = 0;
     TileWalker walk(a, cj, n_tiles);
     int64_t t;
-    uint32_t w0, w1;
-    while (walk.next(t, w0, w1)) {                   // tiles with no passing row are skipped by every role
+    uint32_t wt[NW];
+    while (walk.next(t, wt)) {                       // tiles with no passing row are skipped by every role
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
       ++it;
@@ -541,116 +567,132 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
           }
         }
       }
-      // both halves of the 64-column accumulator are requested back to back, then the buffer is
-      // handed back to the MMA warp before any score is looked at
-      uint32_t vv[2][32];
-      const uint32_t acc_addr = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(buf * kAccCols);
-      tmem_ld_x32(acc_addr, vv[0]);
-      tmem_ld_x32(acc_addr + 32, vv[1]);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(acce_bar(buf), 0));   // the leader issues for both
-        else mbar_arrive(acce_bar(buf));
-      }
-      // Fast reject: once the lists have warmed up almost no tile holds a candidate for any of the
-      // warp's 32 queries.  The largest of the 64 dot products (a tree of 32 three-input max
-      // instructions) is tested against a bound that no candidate can fall below; only if some lane
-      // passes does the warp go on, and then each lane DESCENDS the same tree (7 subtree maxima -> 22
-      // group maxima -> scores) to the few scores that pass instead of testing all 64.
-      float m32[11], n32[11];                        // maxima of groups of 3 scores (columns 0-31 / 32-63)
 #pragma unroll
-      for (int j = 0; j < 10; ++j)
-        m32[j] = fmax3(__uint_as_float(vv[0][3 * j]), __uint_as_float(vv[0][3 * j + 1]), __uint_as_float(vv[0][3 * j + 2]));
-      m32[10] = fmaxf(__uint_as_float(vv[0][30]), __uint_as_float(vv[0][31]));
-#pragma unroll
-      for (int j = 0; j < 10; ++j)
-        n32[j] = fmax3(__uint_as_float(vv[1][3 * j]), __uint_as_float(vv[1][3 * j + 1]), __uint_as_float(vv[1][3 * j + 2]));
-      n32[10] = fmaxf(__uint_as_float(vv[1][30]), __uint_as_float(vv[1][31]));
-      const float t0 = fmax3(m32[0], m32[1], m32[2]), t1 = fmax3(m32[3], m32[4], m32[5]);
-      const float t2 = fmax3(m32[6], m32[7], m32[8]), t3 = fmax3(m32[9], m32[10], n32[0]);
-      const float t4 = fmax3(n32[1], n32[2], n32[3]), t5 = fmax3(n32[4], n32[5], n32[6]);
-      const float t6 = fmax3(n32[7], n32[8], n32[9]);
-      const float best = fmax3(fmax3(t0, t1, t2), fmax3(t3, t4, t5), fmaxf(t6, n32[10]));
-      float lb;                                      // lower bound on the dot product of any candidate of this lane
-      if constexpr (L2) {
-        // d = |q|^2 + |x|^2 - 2 q.x <= tau  =>  q.x >= (|q|^2 + min|x|^2 - tau) / 2 (minus rounding slack),
-        // with min|x|^2 over everything the store ever held (tracked by the upsert kernel): no per-tile loads
-        lb = 0.5f * (base_n - tau) - 4e-7f * (fabsf(base_n) + fabsf(tau));
-      } else {
-        // cosine / ip: fl(1 - dot) <= tau implies dot >= 1 - tau - 2^-24
-        lb = (1.0f - tau) - 1.2e-7f;
-      }
-      if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
-      if constexpr (L2) {
-        // second-level reject with THIS tile's smallest |x|^2 (the store-wide minimum above is loose when the
-        // rows' norms vary; unit-norm embeddings never get further with it)
-        const int64_t r0 = t * kNB + lane, r1 = r0 + 32;
-        const float xn0 = (r0 < a.n_rows) ? __ldg(a.x_norm2 + r0) : __int_as_float(0x7f800000);
-        const float xn1 = (r1 < a.n_rows) ? __ldg(a.x_norm2 + r1) : __int_as_float(0x7f800000);
-        float xmin = fminf(xn0, xn1);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
-        const float bn = qn + xmin;
-        lb = 0.5f * (bn - tau) - 4e-7f * (fabsf(bn) + fabsf(tau));
-        if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
-      }
-      // ---- descent: candidate bits of this lane (a superset; the key comparison below is the exact test) ----
-      uint32_t c0 = 0u, c1 = 0u;
-      if (q_valid && best >= lb) {
-#define RAG_GROUP(GMAX, CBITS, H, G)                                                              \
-        if ((GMAX) >= lb) {                                                                       \
-          if (__uint_as_float(vv[H][3 * (G)]) >= lb) CBITS |= 1u << (3 * (G));                     \
-          if (__uint_as_float(vv[H][3 * (G) + 1]) >= lb) CBITS |= 1u << (3 * (G) + 1);             \
-          if (3 * (G) + 2 < 32 && __uint_as_float(vv[H][(3 * (G) + 2) & 31]) >= lb) CBITS |= 1u << ((3 * (G) + 2) & 31); \
+      for (int sub = 0; sub < NSUB; ++sub) {
+        // both halves of the 64-column accumulator are requested back to back, then the buffer is
+        // handed back to the MMA warp before any score is looked at
+        const uint32_t w0 = wt[2 * sub], w1 = wt[2 * sub + 1];
+        const bool last_sub = (sub == NSUB - 1);
+        uint32_t vv[2][32];
+        const uint32_t acc_addr = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(buf * kAccCols + sub * 64);
+        if ((w0 | w1) != 0u) {                           // a half with no passing row is not even read
+          tmem_ld_x32(acc_addr, vv[0]);
+          tmem_ld_x32(acc_addr + 32, vv[1]);
+          tmem_wait_ld();
         }
-        if (t0 >= lb) { RAG_GROUP(m32[0], c0, 0, 0) RAG_GROUP(m32[1], c0, 0, 1) RAG_GROUP(m32[2], c0, 0, 2) }
-        if (t1 >= lb) { RAG_GROUP(m32[3], c0, 0, 3) RAG_GROUP(m32[4], c0, 0, 4) RAG_GROUP(m32[5], c0, 0, 5) }
-        if (t2 >= lb) { RAG_GROUP(m32[6], c0, 0, 6) RAG_GROUP(m32[7], c0, 0, 7) RAG_GROUP(m32[8], c0, 0, 8) }
-        if (t3 >= lb) { RAG_GROUP(m32[9], c0, 0, 9) RAG_GROUP(m32[10], c0, 0, 10) RAG_GROUP(n32[0], c1, 1, 0) }
-        if (t4 >= lb) { RAG_GROUP(n32[1], c1, 1, 1) RAG_GROUP(n32[2], c1, 1, 2) RAG_GROUP(n32[3], c1, 1, 3) }
-        if (t5 >= lb) { RAG_GROUP(n32[4], c1, 1, 4) RAG_GROUP(n32[5], c1, 1, 5) RAG_GROUP(n32[6], c1, 1, 6) }
-        if (t6 >= lb) { RAG_GROUP(n32[7], c1, 1, 7) RAG_GROUP(n32[8], c1, 1, 8) RAG_GROUP(n32[9], c1, 1, 9) }
-        RAG_GROUP(n32[10], c1, 1, 10)
-#undef RAG_GROUP
-        c0 &= w0;                                    // live & filter bits of the tile's rows
-        c1 &= w1;
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const uint32_t* v = vv[half];
-        uint32_t cand = half ? c1 : c0;
-        while (cand) {
-          const int j = __ffs(cand) - 1;
-          cand &= cand - 1;
-          float sc = 0.0f;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) sc = (jj == j) ? __uint_as_float(v[jj]) : sc;
-          const uint32_t row = static_cast<uint32_t>(t * kNB + half * 32 + j);
-          float dj;
-          if constexpr (L2) dj = fmaxf(fmaf(-2.0f, sc, qn + __ldg(a.x_norm2 + row)), 0.0f);
-          else dj = 1.0f - sc;
-          const uint64_t key = make_key(dj, row);
-          if constexpr (KL > 16) {
-            if (use_q && dj < small_q) {             // keep the own q smallest distances and publish the q-th
-              float x = dj;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { const float c = small[i]; const bool lt = x < c; small[i] = lt ? x : c; x = lt ? c : x; }
-              small_q = small[0];
-#pragma unroll
-              for (int i = 1; i < 8; ++i) small_q = (i == a.tau_q_rank - 1) ? small[i] : small_q;
-              if (small_q < __int_as_float(0x7f800000))
-                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q_row + cj), "r"(float_to_ordered(small_q)) : "memory");
-            }
+        if (last_sub) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(mapa_shared(acce_bar(buf), 0));   // the leader issues for both
+            else mbar_arrive(acce_bar(buf));
           }
-          if (key < kth_key && dj <= tau_g) {
-            top.insert(key, k);
-            kth_key = top.kth(k);
-            if (kth_key != kEmptyKey) {              // list is full: its k-th best bounds the global k-th best
-              const float own = key_dist(kth_key);
-              atomicMin(tau_slot, float_to_ordered(own));
-              tau = fminf(own, tau_g);
+        }
+        if ((w0 | w1) == 0u) continue;
+        if (a.stats && lane == 0) atomicAdd(&g_tensor_stats[0], 1ull);
+        // Fast reject: once the lists have warmed up almost no tile holds a candidate for any of the
+        // warp's 32 queries.  The largest of the 64 dot products (a tree of 32 three-input max
+        // instructions) is tested against a bound that no candidate can fall below; only if some lane
+        // passes does the warp go on, and then each lane DESCENDS the same tree (7 subtree maxima -> 22
+        // group maxima -> scores) to the few scores that pass instead of testing all 64.
+        float m32[11], n32[11];                        // maxima of groups of 3 scores (columns 0-31 / 32-63)
+  #pragma unroll
+        for (int j = 0; j < 10; ++j)
+          m32[j] = fmax3(__uint_as_float(vv[0][3 * j]), __uint_as_float(vv[0][3 * j + 1]), __uint_as_float(vv[0][3 * j + 2]));
+        m32[10] = fmaxf(__uint_as_float(vv[0][30]), __uint_as_float(vv[0][31]));
+  #pragma unroll
+        for (int j = 0; j < 10; ++j)
+          n32[j] = fmax3(__uint_as_float(vv[1][3 * j]), __uint_as_float(vv[1][3 * j + 1]), __uint_as_float(vv[1][3 * j + 2]));
+        n32[10] = fmaxf(__uint_as_float(vv[1][30]), __uint_as_float(vv[1][31]));
+        const float t0 = fmax3(m32[0], m32[1], m32[2]), t1 = fmax3(m32[3], m32[4], m32[5]);
+        const float t2 = fmax3(m32[6], m32[7], m32[8]), t3 = fmax3(m32[9], m32[10], n32[0]);
+        const float t4 = fmax3(n32[1], n32[2], n32[3]), t5 = fmax3(n32[4], n32[5], n32[6]);
+        const float t6 = fmax3(n32[7], n32[8], n32[9]);
+        const float best = fmax3(fmax3(t0, t1, t2), fmax3(t3, t4, t5), fmaxf(t6, n32[10]));
+        float lb;                                      // lower bound on the dot product of any candidate of this lane
+        if constexpr (L2) {
+          // d = |q|^2 + |x|^2 - 2 q.x <= tau  =>  q.x >= (|q|^2 + min|x|^2 - tau) / 2 (minus rounding slack),
+          // with min|x|^2 over everything the store ever held (tracked by the upsert kernel): no per-tile loads
+          lb = 0.5f * (base_n - tau) - 4e-7f * (fabsf(base_n) + fabsf(tau));
+        } else {
+          // cosine / ip: fl(1 - dot) <= tau implies dot >= 1 - tau - 2^-24
+          lb = (1.0f - tau) - 1.2e-7f;
+        }
+        if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
+        if (a.stats && lane == 0) atomicAdd(&g_tensor_stats[1], 1ull);
+        if constexpr (L2) {
+          // second-level reject with THIS tile's smallest |x|^2 (the store-wide minimum above is loose when the
+          // rows' norms vary; unit-norm embeddings never get further with it)
+          const int64_t r0 = t * NB + sub * 64 + lane, r1 = r0 + 32;
+          const float xn0 = (r0 < a.n_rows) ? __ldg(a.x_norm2 + r0) : __int_as_float(0x7f800000);
+          const float xn1 = (r1 < a.n_rows) ? __ldg(a.x_norm2 + r1) : __int_as_float(0x7f800000);
+          float xmin = fminf(xn0, xn1);
+  #pragma unroll
+          for (int off = 16; off > 0; off >>= 1) xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
+          const float bn = qn + xmin;
+          lb = 0.5f * (bn - tau) - 4e-7f * (fabsf(bn) + fabsf(tau));
+          if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
+          if (a.stats && lane == 0) atomicAdd(&g_tensor_stats[2], 1ull);
+        }
+        // ---- descent: candidate bits of this lane (a superset; the key comparison below is the exact test) ----
+        uint32_t c0 = 0u, c1 = 0u;
+        if (q_valid && best >= lb) {
+  #define RAG_GROUP(GMAX, CBITS, H, G)                                                              \
+          if ((GMAX) >= lb) {                                                                       \
+            if (__uint_as_float(vv[H][3 * (G)]) >= lb) CBITS |= 1u << (3 * (G));                     \
+            if (__uint_as_float(vv[H][3 * (G) + 1]) >= lb) CBITS |= 1u << (3 * (G) + 1);             \
+            if (3 * (G) + 2 < 32 && __uint_as_float(vv[H][(3 * (G) + 2) & 31]) >= lb) CBITS |= 1u << ((3 * (G) + 2) & 31); \
+          }
+          if (t0 >= lb) { RAG_GROUP(m32[0], c0, 0, 0) RAG_GROUP(m32[1], c0, 0, 1) RAG_GROUP(m32[2], c0, 0, 2) }
+          if (t1 >= lb) { RAG_GROUP(m32[3], c0, 0, 3) RAG_GROUP(m32[4], c0, 0, 4) RAG_GROUP(m32[5], c0, 0, 5) }
+          if (t2 >= lb) { RAG_GROUP(m32[6], c0, 0, 6) RAG_GROUP(m32[7], c0, 0, 7) RAG_GROUP(m32[8], c0, 0, 8) }
+          if (t3 >= lb) { RAG_GROUP(m32[9], c0, 0, 9) RAG_GROUP(m32[10], c0, 0, 10) RAG_GROUP(n32[0], c1, 1, 0) }
+          if (t4 >= lb) { RAG_GROUP(n32[1], c1, 1, 1) RAG_GROUP(n32[2], c1, 1, 2) RAG_GROUP(n32[3], c1, 1, 3) }
+          if (t5 >= lb) { RAG_GROUP(n32[4], c1, 1, 4) RAG_GROUP(n32[5], c1, 1, 5) RAG_GROUP(n32[6], c1, 1, 6) }
+          if (t6 >= lb) { RAG_GROUP(n32[7], c1, 1, 7) RAG_GROUP(n32[8], c1, 1, 8) RAG_GROUP(n32[9], c1, 1, 9) }
+          RAG_GROUP(n32[10], c1, 1, 10)
+  #undef RAG_GROUP
+          c0 &= w0;                                    // live & filter bits of the tile's rows
+          c1 &= w1;
+          if (a.stats && (c0 | c1)) atomicAdd(&g_tensor_stats[3], static_cast<unsigned long long>(__popc(c0) + __popc(c1)));
+        }
+  #pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* v = vv[half];
+          uint32_t cand = half ? c1 : c0;
+          while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            float sc = 0.0f;
+  #pragma unroll
+            for (int jj = 0; jj < 32; ++jj) sc = (jj == j) ? __uint_as_float(v[jj]) : sc;
+            const uint32_t row = static_cast<uint32_t>(t * NB + sub * 64 + half * 32 + j);
+            float dj;
+            if constexpr (L2) dj = fmaxf(fmaf(-2.0f, sc, qn + __ldg(a.x_norm2 + row)), 0.0f);
+            else dj = 1.0f - sc;
+            const uint64_t key = make_key(dj, row);
+            if constexpr (KL > 16) {
+              if (use_q && dj < small_q) {             // keep the own q smallest distances and publish the q-th
+                if (a.stats) atomicAdd(&g_tensor_stats[5], 1ull);
+                float x = dj;
+  #pragma unroll
+                for (int i = 0; i < 8; ++i) { const float c = small[i]; const bool lt = x < c; small[i] = lt ? x : c; x = lt ? c : x; }
+                small_q = small[0];
+  #pragma unroll
+                for (int i = 1; i < 8; ++i) small_q = (i == a.tau_q_rank - 1) ? small[i] : small_q;
+                if (small_q < __int_as_float(0x7f800000))
+                  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q_row + cj), "r"(float_to_ordered(small_q)) : "memory");
+              }
+            }
+            if (key < kth_key && dj <= tau_g) {
+              if (a.stats) atomicAdd(&g_tensor_stats[4], 1ull);
+              top.insert(key, k);
+              kth_key = top.kth(k);
+              if (kth_key != kEmptyKey) {              // list is full: its k-th best bounds the global k-th best
+                const float own = key_dist(kth_key);
+                atomicMin(tau_slot, float_to_ordered(own));
+                tau = fminf(own, tau_g);
+              }
             }
           }
         }
@@ -673,11 +715,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     uint32_t s = 0, ph = 0;
     TileWalker walk(a, cj, n_tiles, false);
     int64_t t;
-    uint32_t w0, w1;
+    uint32_t wt[NW];
     const int n_sib = (a.progress != nullptr) ? static_cast<int>(gridDim.y) : 1;   // clusters sharing this cj's tiles
     uint32_t* prog = a.progress + static_cast<size_t>(cj) * n_sib;
     uint32_t ti = 0;                                           // tiles this CTA has issued
-    while (walk.next(t, w0, w1)) {
+    while (walk.next(t, wt)) {
       if (n_sib > 1 && (ti & 3u) == 0u) {
         if (crank == 0 && lane == 0)
           asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(prog + blockIdx.y), "r"(0xFFFFFFFFu - ti) : "memory");
@@ -692,13 +734,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         }
       }
       ++ti;
-      const int row0 = static_cast<int>(t * kNB);
+      const int row0 = static_cast<int>(t * NB);
       // optionally pull this CTA's slice of a tile a.prefetch steps ahead into L2 (hides DRAM latency
       // when the CTAs sharing a corpus tile have drifted apart and it is no longer L2-resident)
       {
         const int64_t tp = t + static_cast<int64_t>(a.prefetch) * a.cpm;
         if (a.prefetch > 0 && tp < n_tiles && elect_one()) {
-          const int rp = static_cast<int>(tp * kNB) + static_cast<int>(crank) * (kNB / CL);
+          const int rp = static_cast<int>(tp * NB) + static_cast<int>(crank) * (NB / CL);
           for (int kc = 0; kc < a.row_elems; kc += kAtomK) tma_prefetch_l2_2d(&tmap, kc, rp);
         }
         __syncwarp();
@@ -709,7 +751,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         int atoms = (a.row_elems - k0 + kAtomK - 1) / kAtomK;       // atoms that hold real columns
         atoms = atoms > kAtomsPerStage ? kAtomsPerStage : atoms;
         if (elect_one()) {
-          const int r0 = row0 + static_cast<int>(crank) * (kNB / CL);
+          const int r0 = row0 + static_cast<int>(crank) * (NB / CL);
           if constexpr (PAIR) {
             // the leader's barrier collects the bytes of both halves; each CTA fills its own ring
             const uint32_t lbar = mapa_shared(full_bar(s), 0);
@@ -752,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     tc_fence_after();
     uint32_t s = 0, ph = 0, it = 0;
     const uint64_t desc0 = make_b_desc(base);        // descriptor of stage 0, atom 0, k = 0
-    constexpr uint32_t idesc = PAIR ? kIdescPair : kIdesc;
+    constexpr uint32_t idesc = make_idesc(NB, PAIR ? 2 * kM : kM);
     auto mma = [](uint32_t d, uint32_t at, uint64_t bd, uint32_t acc) {
       if constexpr (PAIR) umma_ts_pair(d, at, bd, idesc, acc);
       else umma_ts(d, at, bd, idesc, acc);
@@ -760,8 +802,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     TileWalker walk(a, cj, (PAIR && crank != 0) ? 0 : n_tiles, false);     // the peer's MMA warps issue nothing
     const uint32_t issuer = (warp == kMmaWarpB) ? 1u : 0u;
     int64_t t;
-    uint32_t w0, w1;
-    while (walk.next(t, w0, w1)) {
+    uint32_t wt[NW];
+    while (walk.next(t, wt)) {
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
       const bool mine = (it & 1u) == issuer;
@@ -862,7 +904,7 @@ EncodeTiledFn get_encode() {
 inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
-  int n_mtiles, cpm, cl, mode;
+  int n_mtiles, cpm, cl, mode, nb;
   size_t off_qbf16, off_qnorm, off_qf32, off_qexact, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
 };
 
@@ -875,6 +917,14 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   // two query tiles or more: CTA pairs (cta_group::2); RAG_B200_TENSOR_MODE=1 selects the older multicast pair
   L.mode = (L.cl == 1) ? 0 : 2;
   if (const char* e = getenv("RAG_B200_TENSOR_MODE")) { if (L.cl == 2 && atoi(e) == 1) L.mode = 1; }
+  // wide (128-row) corpus tiles, possible where tensor memory has room for two 128-column accumulators behind the
+  // A operand (D <= 512) and the CTAs run as pairs.  Measured: 3 % faster at k = 10 on 25M x 384,
+  // 4 % SLOWER at k = 100 and on 10M x 384 -- the per-instruction issue cost it halves is not the bound -- so it is
+  // an experiment switch (RAG_B200_TENSOR_NB=128), off by default.
+  L.nb = kNB;
+  if (L.mode == 2 && ((row_elems + 15) / 16) * 8 + 2 * kNBWide <= kTmemCols &&
+      getenv("RAG_B200_TENSOR_NB") && atoi(getenv("RAG_B200_TENSOR_NB")) == 128)
+    L.nb = kNBWide;
   L.n_mtiles = (L.n_mtiles + L.cl - 1) / L.cl * L.cl;   // pad with idle query tiles to whole clusters
   L.cpm = sm_count / L.n_mtiles;
   if (L.cpm < 1) L.cpm = 1;
@@ -892,19 +942,24 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   return L;
 }
 
-template <int KL, bool L2, int MODE>
+template <int KL, bool L2, int MODE, int NB>
 cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t st) {
   constexpr int CL = (MODE == 0) ? 1 : 2;
-  auto kern = gemm_topk_kernel<KL, L2, MODE>;
+  using R = Ring<MODE, NB>;
+  auto kern = gemm_topk_kernel<KL, L2, MODE, NB>;
   // k <= 16: lists in registers, the whole 224 KB ring.  Larger k: lists in local memory -> a short ring
   // (64-96 KB) and the rest of the SM's 256 KB left to L1
-  a.stages_used = Ring<MODE>::kStages;
-  if (KL > 16) a.stages_used = (MODE == 2) ? 4 : 3;
+  a.stages_used = R::kStages;
+  if (KL > 16) a.stages_used = (96 * 1024) / R::kStageBytes > 4 ? 4 : (96 * 1024) / R::kStageBytes;
   if (const char* ev = getenv("RAG_B200_TENSOR_STAGES")) {
     const int v = atoi(ev);
-    if (v >= 2 && v <= Ring<MODE>::kStages) a.stages_used = v;
+    if (v >= 2 && v <= R::kStages) a.stages_used = v;
   }
-  const int smem_bytes = a.stages_used * Ring<MODE>::kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+  {   // the ring must hold at least one whole tile plus a stage, or producer and issuer wait for each other
+    const int per_tile = (a.row_elems + kStageK - 1) / kStageK;
+    if (a.stages_used < per_tile + 1) a.stages_used = std::min(per_tile + 1, R::kStages);
+  }
+  const int smem_bytes = a.stages_used * R::kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -926,10 +981,12 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
 }
 
 template <int KL>
-cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int mode, dim3 grid, cudaStream_t st) {
-  if (mode == 2) return l2 ? launch_one<KL, true, 2>(tmap, a, grid, st) : launch_one<KL, false, 2>(tmap, a, grid, st);
-  if (mode == 1) return l2 ? launch_one<KL, true, 1>(tmap, a, grid, st) : launch_one<KL, false, 1>(tmap, a, grid, st);
-  return l2 ? launch_one<KL, true, 0>(tmap, a, grid, st) : launch_one<KL, false, 0>(tmap, a, grid, st);
+cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int mode, int nb, dim3 grid, cudaStream_t st) {
+  if (mode == 2 && nb == kNBWide)
+    return l2 ? launch_one<KL, true, 2, kNBWide>(tmap, a, grid, st) : launch_one<KL, false, 2, kNBWide>(tmap, a, grid, st);
+  if (mode == 2) return l2 ? launch_one<KL, true, 2, kNB>(tmap, a, grid, st) : launch_one<KL, false, 2, kNB>(tmap, a, grid, st);
+  if (mode == 1) return l2 ? launch_one<KL, true, 1, kNB>(tmap, a, grid, st) : launch_one<KL, false, 1, kNB>(tmap, a, grid, st);
+  return l2 ? launch_one<KL, true, 0, kNB>(tmap, a, grid, st) : launch_one<KL, false, 0, kNB>(tmap, a, grid, st);
 }
 
 }  // namespace
@@ -987,7 +1044,7 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(width), static_cast<cuuint64_t>(p.n_rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(width) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(kNB / L.cl)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kAtomK), static_cast<cuuint32_t>(L.nb / L.cl)};
   const cuuint32_t estride[2] = {1, 1};
   // 128-byte promotion = exactly the box row (64 bf16); 256 B fetched the neighbouring k-slice early and cost the
   // HBM-bound small batches 4 % (10M x 768, B = 32: 2.565 -> 2.469 ms); no effect at B = 1024
@@ -1008,16 +1065,18 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   a.live = p.live; a.filter = p.filter; a.filter_words = p.filter_words;
   a.n_rows = p.n_rows; a.row_elems = width; a.B = p.B; a.k = kk; a.cpm = L.cpm; a.partial = part;
   a.split_steps = split ? p.row_elems / 16 : 0;
-  a.nbuf = (((width + 15) / 16) * 8 + 4 * kAccCols <= kTmemCols) ? 4 : 2;
+  a.nbuf = (L.nb == kNB && ((width + 15) / 16) * 8 + 4 * kNB <= kTmemCols) ? 4 : 2;
   if (const char* e = getenv("RAG_B200_TENSOR_NBUF")) { if (atoi(e) == 2) a.nbuf = 2; }
   a.dense = p.dense;
+  static const int stats_on = (getenv("RAG_B200_TENSOR_STATS") && atoi(getenv("RAG_B200_TENSOR_STATS")) == 1) ? 1 : 0;
+  a.stats = stats_on;
   a.prefetch = 0;
   if (const char* e = getenv("RAG_B200_TENSOR_PF")) a.prefetch = atoi(e);
   // lists of CTAs that never see a tile must still read as empty
   a.tau_shared = reinterpret_cast<uint32_t*>(p.scratch + L.off_tau);
   a.progress = reinterpret_cast<uint32_t*>(p.scratch + L.off_prog);
   {
-    const size_t tile_bytes = static_cast<size_t>(kNB) * width * 2;
+    const size_t tile_bytes = static_cast<size_t>(L.nb) * width * 2;
     size_t w = kPaceBytes / (static_cast<size_t>(L.cpm) * tile_bytes);
     a.pace_window = static_cast<uint32_t>(w < 8 ? 8 : (w > 4096 ? 4096 : w));
   }
@@ -1039,9 +1098,9 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm * L.cl, L.n_mtiles / L.cl, 1);
   const bool l2 = (p.space == 0);
-  if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.mode, grid, st);
-  else if (kk <= 128) e = launch_kl<128>(tmap, a, l2, L.mode, grid, st);
-  else e = launch_kl<1024>(tmap, a, l2, L.mode, grid, st);
+  if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.mode, L.nb, grid, st);
+  else if (kk <= 128) e = launch_kl<128>(tmap, a, l2, L.mode, L.nb, grid, st);
+  else e = launch_kl<1024>(tmap, a, l2, L.mode, L.nb, grid, st);
   if (e != cudaSuccess) return e;
   out->partial = part;
   out->S = L.cpm;
@@ -1052,6 +1111,15 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   out->merged = reinterpret_cast<uint64_t*>(p.scratch + L.off_merged);
   if (launches) *launches += 2;
   return cudaSuccess;
+}
+
+int read_stats(unsigned long long* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, g_tensor_stats, 8 * sizeof(unsigned long long)) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  if (reset) {
+    const unsigned long long z[8] = {};
+    if (cudaMemcpyToSymbol(g_tensor_stats, z, sizeof(z)) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+  }
+  return 0;
 }
 
 }  // namespace tensor

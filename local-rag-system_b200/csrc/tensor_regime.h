@@ -49,6 +49,8 @@ struct Result {
   const float* q_exact;     // [B][exact_elems] normalised, un-rounded queries (Problem::rerank)
   uint64_t* merged;         // [B][k_kept] scratch for the merged keys before refinement
 };
+// epilogue selection counters (RAG_B200_TENSOR_STATS=1), see tensor_regime.cu
+int read_stats(unsigned long long* out8, int reset);
 // Runs prep + contraction + fused select.
 cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches);
 

@@ -174,3 +174,85 @@ def test_mask_cache_is_invalidated_by_writes(client):
     for j in range(40):   # more distinct filters than device mask slots
         assert col.query(query_embeddings=[[0, 1]], n_results=5, where={"t": f"v{j}"})["ids"] == [[]]
     assert col.query(query_embeddings=[[0, 1]], n_results=5, where=w)["ids"] == [["b"]]
+
+
+def test_cached_masks_are_patched_not_rebuilt(client):
+    """A write changes only the written rows' bits of every cached `where` bitmap (Collection._patch_masks);
+    the predicate is evaluated over all rows once, however many writes and searches follow."""
+    col = client.get_or_create_collection("p")
+    col.add(ids=[f"a{j}" for j in range(50)], embeddings=[[float(j), 1.0] for j in range(50)],
+            metadatas=[{"t": "x" if j % 2 else "y", "n": j} for j in range(50)])
+    w1, w2 = {"t": "x"}, {"n": {"$lt": 10}}
+    st = col._s
+    assert len(col.query(query_embeddings=[[0, 1]], n_results=50, where=w1)["ids"][0]) == 25
+    assert len(col.query(query_embeddings=[[0, 1]], n_results=50, where=w2)["ids"][0]) == 10
+    assert st.mask_uploads == 2
+    for j in range(50, 80):
+        col.add(ids=[f"a{j}"], embeddings=[[float(j), 1.0]], metadatas=[{"t": "x", "n": j % 20}])
+        assert f"a{j}" in col.query(query_embeddings=[[float(j), 1.0]], n_results=3, where=w1)["ids"][0]
+    assert len(col.query(query_embeddings=[[0, 1]], n_results=100, where=w1)["ids"][0]) == 55
+    assert len(col.query(query_embeddings=[[0, 1]], n_results=100, where=w2)["ids"][0]) == 10 + 10
+    col.update(ids=["a1"], metadatas=[{"t": "y"}])
+    col.delete(ids=["a3"])
+    col.add(ids=["b"], embeddings=[[3.0, 1.0]], metadatas=[{"t": "y", "n": 99}])        # takes a3's row: bit must clear
+    got = col.query(query_embeddings=[[0, 1]], n_results=100, where=w1)["ids"][0]
+    assert "a1" not in got and "a3" not in got and "b" not in got and len(got) == 53
+    assert st.mask_uploads == 2 and st.mask_patches > 0
+    # a bulk write beyond the patch limit invalidates instead (one re-evaluation at the next query)
+    big = 5000
+    col.add(ids=[f"c{j}" for j in range(big)], embeddings=np.ones((big, 2), np.float32), metadatas=[{"t": "x"}] * big)
+    assert len(col.query(query_embeddings=[[0, 1]], n_results=10, where=w1)["ids"][0]) == 10
+    assert st.mask_uploads == 3
+
+
+def test_upsert_merges_metadata_and_keeps_the_document(client):
+    """Chroma's metadata segment applies an UPSERT of an existing id as an update: keys given are replaced,
+    keys not given stay, the document stays when none is passed [dep: chromadb 0.5.3 _update_metadata]."""
+    col = client.get_or_create_collection("u")
+    col.upsert(ids=["a"], embeddings=[[1.0, 0.0]], metadatas=[{"k1": "v1", "k2": 2}], documents=["doc a"])
+    col.upsert(ids=["a"], embeddings=[[0.0, 1.0]], metadatas=[{"k2": 3, "k3": True}])
+    got = col.get(ids=["a"], include=["metadatas", "documents", "embeddings"])
+    assert got["metadatas"] == [{"k1": "v1", "k2": 3, "k3": True}] and got["documents"] == ["doc a"]
+    assert np.allclose(got["embeddings"][0], [0.0, 1.0])
+    col.upsert(ids=["a"], embeddings=[[0.0, 1.0]], documents=["doc b"])
+    got = col.get(ids=["a"])
+    assert got["metadatas"] == [{"k1": "v1", "k2": 3, "k3": True}] and got["documents"] == ["doc b"]
+    assert col.query(query_embeddings=[[0, 1]], n_results=1, where={"k1": "v1"})["ids"] == [["a"]]
+
+
+def test_device_list_metadata():
+    from local_rag_system_b200.collection import _parse_devices
+    assert _parse_devices("0-7") == list(range(8))
+    assert _parse_devices("0,2,4") == [0, 2, 4]
+    assert _parse_devices("0-1, 4-5") == [0, 1, 4, 5]
+    assert _parse_devices([1, 3]) == [1, 3] and _parse_devices(2) == [2]
+    assert _parse_devices(None) is None and _parse_devices("") is None
+
+
+def test_persistence_semantics(monkeypatch, tmp_path):
+    """Journal: a dropped collection is not resurrected from a Chroma file in the same directory; the stored
+    space / dtype win over a later caller's; vector-less update records replay as metadata updates."""
+    from local_rag_system_b200 import persist
+    from local_rag_system_b200.collection import _reset_registry_for_tests
+    monkeypatch.setattr(colmod, "DeviceStore", FakeDeviceStore)
+    path = str(tmp_path / "store")
+    col = rag.PersistentClient(path=path).get_or_create_collection("c", metadata={"hnsw:space": "cosine"})
+    col.add(ids=["a", "b"], embeddings=[[1.0, 0.0], [0.0, 1.0]], metadatas=[{"t": 1}, {"t": 2}], documents=["da", "db"])
+    col.update(ids=["a"], metadatas=[{"u": 5}])
+    _reset_registry_for_tests()
+    col2 = rag.PersistentClient(path=path).get_or_create_collection("c", metadata={"hnsw:space": "l2"})
+    assert col2._s.space == "cosine"                     # the journal was written under cosine
+    assert col2.get(ids=["a"])["metadatas"] == [{"t": 1, "u": 5}] and col2.count() == 2
+    # a vector-less Chroma "update" record
+    state = col2._s
+    persist._replay(state, [("update", "b", None, {"t": 9}, None)])
+    assert col2.get(ids=["b"])["metadatas"] == [{"t": 9}] and col2.get(ids=["b"])["documents"] == ["db"]
+    client = rag.PersistentClient(path=path)
+    client.delete_collection("c")
+    _reset_registry_for_tests()
+    j = persist.Journal(str(tmp_path / "store" / persist.JOURNAL_FILE), "c")
+    assert j.was_dropped() and j.stored_metadata() == (None, False)
+    j.close()
+    col3 = rag.PersistentClient(path=path).get_or_create_collection("c")
+    assert col3.count() == 0
+    _reset_registry_for_tests()

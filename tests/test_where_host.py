@@ -102,3 +102,47 @@ def test_where_document():
     for bad in [{"$contains": ""}, {"$like": "x"}, {"$contains": 3}, "x"]:
         with pytest.raises(ValueError):
             validate_where_document(bad)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_single_record_matcher_agrees_with_the_column_compiler(seed):
+    """match_record (used to patch cached bitmaps row by row after a write) must decide every record exactly
+    as MetadataColumns.evaluate decides it in bulk."""
+    import random
+    from local_rag_system_b200.where import MetadataColumns, match_record
+    rng = random.Random(100 + seed)
+    keys = ["namespace", "n", "score", "flag"]
+    metas = []
+    for _ in range(300):
+        m = {}
+        if rng.random() < 0.8:
+            m["namespace"] = rng.choice(["history", "docs", "x"])
+        if rng.random() < 0.7:
+            m["n"] = rng.randint(0, 9)
+        if rng.random() < 0.5:
+            m["score"] = rng.choice([0.5, 1.5, 2.0])
+        if rng.random() < 0.4:
+            m["flag"] = rng.random() < 0.5
+        if rng.random() < 0.1:
+            m["n"] = "seven"              # another type under the same key
+        metas.append(m or None)
+    cols = MetadataColumns()
+    for r, m in enumerate(metas):
+        cols.set_row(r, None, m)
+    wheres = [{"namespace": "history"}, {"n": {"$lt": 5}}, {"n": {"$gte": 3, "$lte": 7}}, {"score": {"$gt": 1.0}},
+              {"flag": True}, {"flag": {"$ne": True}}, {"namespace": {"$in": ["docs", "x"]}}, {"n": {"$nin": [1, 2, 3]}},
+              {"namespace": "history", "n": 3}, {"$or": [{"n": 1}, {"namespace": "x"}]},
+              {"$and": [{"namespace": {"$ne": "x"}}, {"$or": [{"score": 2.0}, {"n": {"$gt": 6}}]}]}, {"missing": 1},
+              {"missing": {"$ne": 1}}, {"n": "seven"}, {"n": 7}, {"score": {"$lt": 2}}]
+    for w in wheres:
+        bulk = cols.evaluate(w, len(metas))
+        one = np.array([match_record(w, m) for m in metas])
+        assert np.array_equal(bulk, one), w
+
+
+def test_single_document_matcher():
+    from local_rag_system_b200.where import evaluate_where_document, match_document
+    docs = np.array(["alpha beta", None, "beta", "gamma"], dtype=object)
+    for wd in ({"$contains": "beta"}, {"$not_contains": "beta"}, {"$or": [{"$contains": "alpha"}, {"$contains": "gamma"}]},
+               {"$and": [{"$contains": "beta"}, {"$not_contains": "alpha"}]}):
+        assert np.array_equal(evaluate_where_document(wd, docs, 4), np.array([match_document(wd, d) for d in docs])), wd
