@@ -258,6 +258,7 @@ constexpr uint32_t make_idesc(int n, int m) {
 __device__ unsigned long long g_tensor_stats[8];
 
 struct Args {
+  int lists_in_smem;             // 16 < k <= 128: the per-thread heaps live in shared memory behind the barriers
   int stats;                     // 1: count into g_tensor_stats (debug; costs a few atomics per slow-path tile)
   const __nv_bfloat16* q_bf16;   // [n_mtiles*128][row_elems] prepared queries, zero rows beyond B
   const float* q_norm2;          // [n_mtiles*128]
@@ -296,30 +297,53 @@ struct Args {
 };
 constexpr size_t kPaceBytes = 56u << 20;  // L2 budget (of 126 MB) for the tiles between the slowest and the fastest sibling
 
-// per-thread running top-k.  KL <= 16: sorted list, fully unrolled (registers / L1-resident);
-// larger k: a binary MAX-heap in local memory (root = current k-th best): an insertion is a
-// root replacement + sift-down, O(log k) instead of the O(k) shift of a sorted list -- with
-// k = 100 the sorted list made the epilogue, not the tensor pipe, the bottleneck.
+// per-thread running top-k.
+//   KL <= 16        sorted list, fully unrolled, in registers;
+//   16 < KL <= 128  a binary MAX-heap (root = current k-th best; an insertion is a root replacement + sift-down,
+//                   O(log k) instead of the O(k) shift of a sorted list) in SHARED memory behind the barriers,
+//                   entry i of epilogue thread t at word i * 128 + t (the 32 lanes of a warp touch consecutive
+//                   words).  In local memory the same heap cost 4 % more (25M x 384, k = 100: 24.1 -> 23.1 ms);
+//                   falls back to local memory for the rare shapes whose block does not fit next to the ring (one
+//                   query tile, D = 768, k > 96).  A warp-cooperative SORTED list (all 32 lanes insert one
+//                   candidate together, candidates of different lanes one after the other) was measured too and
+//                   is slower (25.1 ms): a tile's ~7 candidates sit in different lanes, whose private sift-downs
+//                   run side by side.
+//   KL  > 128       the same heap in local memory (1024 x 8 B x 128 threads does not fit on chip).
+constexpr int kEpiThreads = 128;
+constexpr int kSmemListMax = 128;
 template <int KL>
 struct TopList {
-  uint64_t e[KL];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < KL; ++i) e[i] = kEmptyKey;
+  static constexpr bool kRegs = (KL <= 16);
+  static constexpr bool kShared = (KL > 16 && KL <= kSmemListMax);
+  uint64_t e[KL];                                      // (kShared: only used when the block did not fit, see launch_one)
+  uint64_t* sh;                                        // kShared: this thread's column of the CTA's list block, or nullptr
+  __device__ __forceinline__ uint64_t& at(int i) {
+    if constexpr (kShared) return sh != nullptr ? sh[i * kEpiThreads] : e[i];
+    else return e[i];
   }
-  __device__ __forceinline__ uint64_t kth(int k) const {
-    if constexpr (KL <= 16) {
+  __device__ __forceinline__ void init(uint64_t* block, int tid, int k) {
+    if constexpr (kShared) {
+      sh = block != nullptr ? block + tid : nullptr;
+      for (int i = 0; i < k; ++i) at(i) = kEmptyKey;
+    } else {
+      sh = nullptr;
+#pragma unroll
+      for (int i = 0; i < KL; ++i) e[i] = kEmptyKey;
+    }
+  }
+  __device__ __forceinline__ uint64_t kth(int k) {
+    if constexpr (kRegs) {
       uint64_t t = e[KL - 1];
 #pragma unroll
       for (int i = 0; i < KL; ++i) t = (i == k - 1) ? e[i] : t;
       return t;
     } else {
-      return e[0];
+      return at(0);
     }
   }
   // precondition: key < kth(k)
   __device__ __forceinline__ void insert(uint64_t key, int k) {
-    if constexpr (KL <= 16) {
+    if constexpr (kRegs) {
 #pragma unroll
       for (int i = 0; i < KL; ++i) {
         const uint64_t cur = e[i];
@@ -328,40 +352,31 @@ struct TopList {
         key = lt ? cur : key;
       }
     } else {
-      int i = 0;
-      for (;;) {                       // sift the new key down from the root
-        const int l = 2 * i + 1, r = l + 1;
-        if (l >= k) break;
-        const uint64_t lv = e[l];
-        const uint64_t rv = (r < k) ? e[r] : 0ull;
-        const int c = (rv > lv) ? r : l;
-        const uint64_t cv = (rv > lv) ? rv : lv;
-        if (cv <= key) break;
-        e[i] = cv;
-        i = c;
-      }
-      e[i] = key;
+      sift(key, k);
     }
   }
-  // ascending order in e[0..k) (heap sort for the heap variant; the list already is)
+  __device__ __forceinline__ void sift(uint64_t key, int n) {      // sift `key` down from the root of a heap of n
+    int i = 0;
+    for (;;) {
+      const int l = 2 * i + 1, r = l + 1;
+      if (l >= n) break;
+      const uint64_t lv = at(l);
+      const uint64_t rv = (r < n) ? at(r) : 0ull;
+      const int c = (rv > lv) ? r : l;
+      const uint64_t cv = (rv > lv) ? rv : lv;
+      if (cv <= key) break;
+      at(i) = cv;
+      i = c;
+    }
+    at(i) = key;
+  }
+  // ascending order in slots 0..k) (heap sort for the heap variants; the register list already is)
   __device__ __forceinline__ void finalize(int k) {
-    if constexpr (KL > 16) {
+    if constexpr (!kRegs) {
       for (int n = k - 1; n > 0; --n) {
-        const uint64_t key = e[n];     // move the max to its final slot, re-insert the displaced key
-        e[n] = e[0];
-        int i = 0;
-        for (;;) {
-          const int l = 2 * i + 1, r = l + 1;
-          if (l >= n) break;
-          const uint64_t lv = e[l];
-          const uint64_t rv = (r < n) ? e[r] : 0ull;
-          const int c = (rv > lv) ? r : l;
-          const uint64_t cv = (rv > lv) ? rv : lv;
-          if (cv <= key) break;
-          e[i] = cv;
-          i = c;
-        }
-        e[i] = key;
+        const uint64_t key = at(n);    // move the max to its final slot, re-insert the displaced key
+        at(n) = at(0);
+        sift(key, n);
       }
     }
   }
@@ -519,9 +534,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       asm volatile("bar.sync 1, 192;" ::: "memory");   // epilogue warps (128) + both MMA warps (64): A operand is in TMEM
     }
 
-    TopList<KL> top;
-    top.init();
     const int k = a.k;
+    TopList<KL> top;
+    top.init(a.lists_in_smem ? reinterpret_cast<uint64_t*>(smem_raw + (bar_base + 512u - raw)) : nullptr, lg * 32 + lane, k);
     float tau = __int_as_float(0x7f800000);          // rejection threshold: min(own k-th best, shared bound); +inf at first
     float tau_g = __int_as_float(0x7f800000);        // last shared bound seen
     uint64_t kth_key = kEmptyKey;
@@ -706,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < KL; ++i) if (i < k) out[i] = top.e[i];
       } else {
-        for (int i = 0; i < k; ++i) out[i] = top.e[i];
+        for (int i = 0; i < k; ++i) out[i] = top.at(i);
       }
     }
     tc_fence_before();
@@ -947,23 +962,28 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
   constexpr int CL = (MODE == 0) ? 1 : 2;
   using R = Ring<MODE, NB>;
   auto kern = gemm_topk_kernel<KL, L2, MODE, NB>;
-  // k <= 16: lists in registers, the whole 224 KB ring.  Larger k: lists in local memory -> a short ring
-  // (64-96 KB) and the rest of the SM's 256 KB left to L1
+  // k <= 16: lists in registers, the whole 224 KB ring.  16 < k <= 128: the heaps take k x 128 x 8 bytes of shared
+  // memory behind the barriers, the ring gets what is left (>= 96 KB; its depth does not limit the kernel: 4 stages
+  // measured as fast as 14).  Larger k: heaps in local memory -> a short ring and the rest of the SM left to L1.
+  const int per_tile = (a.row_elems + kStageK - 1) / kStageK;
+  int list_bytes = TopList<KL>::kShared ? a.k * kEpiThreads * 8 : 0;
+  if (list_bytes > 0 && (kRingBytes - list_bytes) / R::kStageBytes < per_tile + 1) list_bytes = 0;   // no room: heaps in local memory
+  a.lists_in_smem = list_bytes > 0 ? 1 : 0;
   a.stages_used = R::kStages;
-  if (KL > 16) a.stages_used = (96 * 1024) / R::kStageBytes > 4 ? 4 : (96 * 1024) / R::kStageBytes;
+  if (list_bytes > 0) a.stages_used = std::min(R::kStages, (kRingBytes - list_bytes) / R::kStageBytes);
+  else if (KL > 16) a.stages_used = std::min(4, (96 * 1024) / R::kStageBytes);
   if (const char* ev = getenv("RAG_B200_TENSOR_STAGES")) {
     const int v = atoi(ev);
-    if (v >= 2 && v <= R::kStages) a.stages_used = v;
+    if (v >= 2 && v <= a.stages_used) a.stages_used = v;
   }
-  {   // the ring must hold at least one whole tile plus a stage, or producer and issuer wait for each other
-    const int per_tile = (a.row_elems + kStageK - 1) / kStageK;
-    if (a.stages_used < per_tile + 1) a.stages_used = std::min(per_tile + 1, R::kStages);
-  }
-  const int smem_bytes = a.stages_used * R::kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
+  // the ring must hold at least one whole tile plus a stage, or producer and issuer wait for each other
+  if (a.stages_used < per_tile + 1) a.stages_used = std::min(per_tile + 1, R::kStages);
+  const int smem_bytes = a.stages_used * R::kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + list_bytes;
+  if (smem_bytes > kSmemBytes) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                           (KL > 16) ? std::min(100, (smem_bytes + 8 * 1024) * 100 / (228 * 1024) + 1) : 100);
+                           (KL > 16 && list_bytes == 0) ? std::min(100, (smem_bytes + 8 * 1024) * 100 / (228 * 1024) + 1) : 100);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;

@@ -308,6 +308,9 @@ TENSOR_CASES = [
     ("cosine", 2500, 72, 300, 3),         # K = 72: second atom mostly out of bounds
     ("ip", 1500, 8, 5, 7),                # smallest row (one 16-byte chunk)
     ("cosine", 20000, 768, 1024, 10),     # the headline batch shape on a small corpus
+    ("cosine", 6000, 768, 200, 100),      # CTA pairs, 768-wide A operand (2 accumulators), heaps in shared memory
+    ("l2", 3000, 768, 30, 100),           # one query tile, 768-d, k = 100: the heap block does not fit -> local memory
+    ("ip", 5000, 512, 260, 120),          # three query tiles (one idle), k = 120
 ]
 
 
