@@ -67,6 +67,7 @@ extern "C" {
 #define RAG_MAX_MASK_SLOTS 16
 
 typedef struct rag_store rag_store;
+typedef struct rag_exchange rag_exchange;
 
 RAG_API const char* rag_last_error(void);
 RAG_API int rag_abi_version(void);
@@ -179,6 +180,17 @@ RAG_API int rag_store_query_dev(rag_store* s, int B, const float* queries_dev, i
                         int64_t* out_rows_dev, float* out_dists_dev, int32_t* out_counts_dev,
                         void* stream);
 
+/* Host-buffer queries IN FLIGHT: what a server with concurrent requests does.  submit() stages the queries in
+ * pinned memory, copies them down and launches the search on the store's pipeline stream, and returns a ticket
+ * at once; wait() blocks until that query's result is on the host.  Up to 4 tickets may be outstanding; the
+ * copy + launch of request i+1 then overlaps the scan of request i, and consecutive scans overlap by programmatic
+ * dependent launch.  With an exchange (x != NULL; every rank submits the same sequence) this is the multi-GPU
+ * fused search of rag_store_query_fused; with x == NULL the single-store search of rag_store_query.       */
+RAG_API int rag_store_query_submit(rag_store* s, rag_exchange* x, int B, const float* queries, int k,
+                           int mask_slot, int flags, uint32_t row_base, int* ticket);
+RAG_API int rag_store_query_wait(rag_store* s, int ticket, int64_t* out_rows, float* out_dists,
+                         int32_t* out_counts);
+
 /* Cross-shard merge (after the NCCL all-gather of per-shard candidates):
  * keys_dev is G x B x k (each list ascending).  Writes B x k global rows /
  * distances and B counts on the device; any output pointer may be NULL.      */
@@ -204,7 +216,6 @@ RAG_API int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* 
  * (stream regime, k <= 128, B * k <= slot_keys); otherwise use rag_store_query_dev +
  * all-gather + rag_merge_keys_dev.                                                 */
 #define RAG_EXCHANGE_HANDLE_BYTES 64
-typedef struct rag_exchange rag_exchange;
 RAG_API int rag_exchange_create(int device, int rank, int world, int64_t slot_keys, rag_exchange** out);
 RAG_API int rag_exchange_handle(rag_exchange* x, void* out_handle);
 RAG_API int rag_exchange_connect(rag_exchange* x, const void* handles);

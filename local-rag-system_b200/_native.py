@@ -71,6 +71,8 @@ SIGNATURES = {
     "rag_store_fused_ok": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int]),
     "rag_store_query_fused_dev": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p, _p]),
     "rag_store_query_fused": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _p, _p, _p]),
+    "rag_store_query_submit": (C.c_int, [_p, _p, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_uint32, _i32p]),
+    "rag_store_query_wait": (C.c_int, [_p, C.c_int, _p, _p, _p]),
     "rag_sharded_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int64, C.c_int, C.POINTER(_p)]),
     "rag_sharded_destroy": (C.c_int, [_p]),
     "rag_sharded_shards": (C.c_int, [_p]),

@@ -22,6 +22,9 @@
 //   R x NJ independent 16-byte streaming loads (no L1 allocation) before the
 //   first FMA, so 16 resident warps/SM keep ~96 KB/SM in flight.
 #include <stdlib.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -96,8 +99,15 @@ __device__ __forceinline__ float chunk_acc(float acc, const uint4& v, const floa
 // every lane busy; the 32/LPR sub-warps of a warp work on different rows).  NJ > 0: a row is
 // exactly NJ x LPR chunks (fully unrolled, no guards); NJ == 0: any row length (LPR = 32).
 // R row slots in flight per warp, i.e. R x 32/LPR rows.
-template <bool BF16, int QB, int NJ, int R, bool L2, int LPR>
-__global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const ScanArgs a) {
+struct InlineQuery { float v[kInlineQueryMax]; };
+static_assert(sizeof(ScanArgs) + sizeof(InlineQuery) <= 4096, "the inline query must keep the launch parameters within 4 KB");
+struct NoInlineQuery {};
+
+// INLQ: the (single) raw query arrives in the launch parameters (`iq`), not in global memory.
+template <bool BF16, int QB, int NJ, int R, bool L2, int LPR, bool INLQ>
+__global__ void __launch_bounds__(kScanThreads, 2)
+scan_stream_kernel(const ScanArgs a, const std::conditional_t<INLQ, InlineQuery, NoInlineQuery> iq) {
+  static_assert(!INLQ || QB == 1, "only a single query rides in the launch parameters");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int V = R * QB;
   constexpr int G = 32 / LPR;                      // rows per slot
@@ -131,13 +141,19 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   // lane-strided summation order -> bit-identical values in both regimes): cosine stores scale
   // by 1/|q|, bf16 stores round to bf16.
   __shared__ float s_scale[QB];
-  if (a.queries_raw != nullptr) {
+  // element e of raw query `bs` (parameter space is indexed directly: taking its address would copy it to local memory)
+  auto raw_q = [&](int bs, int e) -> float {
+    if constexpr (INLQ) { (void)bs; return iq.v[e]; }
+    else return a.queries_raw[static_cast<size_t>(bs) * a.dim + e];
+  };
+  const bool have_raw = INLQ || a.queries_raw != nullptr;
+  if (have_raw) {
     if (warp < QB) {
       const int b = b0 + warp;
       float ss = 0.0f;
       if (a.normalise && b < nB) {
-        const float* src = a.queries_raw + static_cast<size_t>(a.q_index ? a.q_index[b] : b) * a.dim;
-        for (int e = lane; e < a.dim; e += 32) { const float x = src[e]; ss = fmaf(x, x, ss); }
+        const int bs = a.q_index ? a.q_index[b] : b;
+        for (int e = lane; e < a.dim; e += 32) { const float x = raw_q(bs, e); ss = fmaf(x, x, ss); }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
       }
@@ -150,9 +166,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     int b = b0 + qb;
     float val = 0.0f;
     if (b < nB) {
-      if (a.queries_raw != nullptr) {
+      if (have_raw) {
         const int bs = a.q_index ? a.q_index[b] : b;
-        val = (e < a.dim) ? a.queries_raw[static_cast<size_t>(bs) * a.dim + e] * s_scale[qb] : 0.0f;
+        val = (e < a.dim) ? raw_q(bs, e) * s_scale[qb] : 0.0f;
         if (a.round_bf16) val = __bfloat162float(__float2bfloat16_rn(val));
       } else {
         val = a.queries[static_cast<size_t>(b) * row_elems + e];
@@ -502,7 +518,6 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       // is read and rewritten only by warp j % 8 -- then sort again; the best k_out are emitted.
       __syncthreads();
       const int bs_q = a.q_index ? a.q_index[b] : b;
-      const float* qraw = a.queries_raw + static_cast<size_t>(bs_q) * a.dim;
       const float qscale = s_scale[qb];
       for (int j = warp; j < k; j += kScanWarps) {
         const uint64_t key = sorted[j];
@@ -511,7 +526,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         const float* xr = a.exact + static_cast<size_t>(row) * a.exact_elems;
         float acc = 0.0f;
         for (int e = lane; e < a.dim; e += 32) {
-          const float qv = qraw[e] * qscale;
+          const float qv = raw_q(bs_q, e) * qscale;
           const float xv = __ldg(xr + e);
           if constexpr (L2) { const float d = xv - qv; acc = fmaf(d, d, acc); }
           else acc = fmaf(xv, qv, acc);
@@ -654,8 +669,8 @@ size_t scan_total_smem(int QB, int row_elems, int k, int grid_x, int* merge_cap)
   return need;
 }
 
-template <typename Kern>
-cudaError_t launch_pdl(Kern kern, const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+template <typename Kern, typename IQ>
+cudaError_t launch_pdl(Kern kern, const ScanArgs& a, const IQ& iq, dim3 grid, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -671,13 +686,21 @@ cudaError_t launch_pdl(Kern kern, const ScanArgs& a, dim3 grid, size_t smem, cud
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, a);
+  return cudaLaunchKernelEx(&cfg, kern, a, iq);
 }
 
 template <bool BF16, int QB, int NJ, int R, int LPR>
 cudaError_t launch_one(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR>, a, grid, smem, st);
-  return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR>, a, grid, smem, st);
+  if constexpr (QB == 1) {
+    if (a.inline_host != nullptr) {          // the query rides in the launch parameters
+      InlineQuery iq;
+      memcpy(iq.v, a.inline_host, static_cast<size_t>(a.dim) * sizeof(float));
+      if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR, true>, a, iq, grid, smem, st);
+      return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR, true>, a, iq, grid, smem, st);
+    }
+  }
+  if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR, false>, a, NoInlineQuery{}, grid, smem, st);
+  return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR, false>, a, NoInlineQuery{}, grid, smem, st);
 }
 
 template <bool BF16, int QB>
@@ -725,6 +748,7 @@ int scan_stream_max_qb(int dtype, int row_elems, int k) {
 
 cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st, int* launches) {
   if (a.B <= 0 || a.k <= 0) return cudaErrorInvalidValue;
+  if (a.inline_host != nullptr && (a.B != 1 || a.dim > kInlineQueryMax || a.q_index != nullptr)) return cudaErrorInvalidValue;
   const int max_qb = scan_stream_max_qb(a.dtype, a.row_elems, a.k);
   int QB = 1;
   while (QB < a.B && QB < max_qb) QB <<= 1;

@@ -66,6 +66,28 @@ struct PendingWrites {
   bool in_flight = false;
 };
 
+// Host-buffer queries in flight (rag_store_query_submit / _wait): a server keeps a few requests in the air,
+// so the copy + launch of request i+1 overlaps the scan of request i and consecutive scans overlap by
+// programmatic dependent launch -- what the device-resident back-to-back loop measures, through host buffers.
+struct PipeSlot {
+  unsigned char* h = nullptr;      // pinned: queries | rows | dists | counts | flag
+  unsigned char* d = nullptr;      // device mirror
+  size_t bytes = 0;
+  cudaEvent_t ev = nullptr;        // behind the slot's last device-to-host copy (when the flag path is not used)
+  uint32_t seq = 0;
+  bool busy = false, armed = false;
+  int B = 0, k = 0;
+  size_t in_b = 0, rows_b = 0, dist_b = 0, cnt_b = 0;
+};
+struct Pipeline {
+  static constexpr int kSlots = 4;
+  cudaStream_t stream = nullptr;
+  QueryCtx* ctx = nullptr;         // registered with the store like any asynchronous reader (scratch, write ordering)
+  PipeSlot slot[kSlots];
+  uint32_t next = 0;
+  std::mutex mu;
+};
+
 struct SearchOut {
   uint64_t* keys = nullptr;
   int64_t* rows = nullptr;
@@ -135,6 +157,7 @@ struct rag_store {
   cudaEvent_t ev_write = nullptr;         // recorded behind the last device-side write
   std::atomic<uint64_t> write_seq{0};
   rag::PendingWrites pending;
+  rag::Pipeline* pipe = nullptr;
   std::atomic<int64_t> pending_n{0};
   std::atomic<int64_t> launches{0};
   std::atomic<int> last_regime{0};
@@ -149,9 +172,12 @@ namespace rag {
 // read lock held by the caller.  Orders the context's stream behind the last write, runs the regime's
 // kernels asynchronously on c->stream.  `scratch` must hold search_scratch_bytes().
 size_t search_scratch_bytes(const rag_store* s, int B, int k, int grid_x);
+// h_inline (may be NULL): the same queries in HOST memory; where inline_query_ok() holds the single query then
+// rides in the launch parameters and d_queries_raw is not read (the caller need not have copied it down).
 int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
                   int mask_slot, int regime, RowMap rows_map, const SearchOut& out, bool timed,
-                  rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor);
+                  rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor, const float* h_inline = nullptr);
+bool inline_query_ok(const rag_store* s, int B, int regime);
 int choose_regime(const rag_store* s, int B, int k, int flags);
 int batch_limit(const rag_store* s, int k);
 int check_query_args(const rag_store* s, int B, const void* q, int k, int mask_slot);

@@ -203,6 +203,28 @@ class DeviceStore:
                                                 int(row_base), _ptr(rows), _ptr(dists), _ptr(counts)))
         return rows, dists, counts
 
+    def submit(self, queries, k: int, mask_slot: int = -1, regime: str = "auto", exchange: "Exchange" = None,
+               row_base: int = 0):
+        """Start a host-buffer query and return at once (rag_store_query_submit); up to 4 may be in flight.
+        Returns a ticket for collect().  With `exchange` this is the fused multi-GPU search."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
+        t = C.c_int32(-1)
+        N.check(self._lib.rag_store_query_submit(self._h, exchange.handle if exchange is not None else None, q.shape[0],
+                                                 _ptr(q), int(k), int(mask_slot), flags, int(row_base), C.byref(t)))
+        return (t.value, q.shape[0], int(k))
+
+    def collect(self, ticket):
+        """Wait for a submitted query; returns numpy (rows, dists, counts)."""
+        t, B, k = ticket
+        rows = np.empty((B, k), dtype=np.int64)
+        dists = np.empty((B, k), dtype=np.float32)
+        counts = np.empty(B, dtype=np.int32)
+        N.check(self._lib.rag_store_query_wait(self._h, int(t), _ptr(rows), _ptr(dists), _ptr(counts)))
+        return rows, dists, counts
+
     def fused_ok(self, exchange: "Exchange", B: int, k: int, regime: str = "auto") -> bool:
         flags = {"auto": N.QUERY_AUTO, "stream": N.QUERY_FORCE_STREAM, "tensor": N.QUERY_FORCE_TENSOR}[regime]
         return bool(self._lib.rag_store_fused_ok(self._h, exchange.handle, int(B), int(k), flags))

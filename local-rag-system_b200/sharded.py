@@ -152,6 +152,25 @@ class ShardedSearcher:
                           b["dists"].data_ptr(), b["counts"].data_ptr(), stream=stream)
         return b["rows"], b["dists"], b["counts"]
 
+    def submit(self, queries: np.ndarray, k: int, mask_slot: int = -1, regime: str = "auto"):
+        """Start a host-to-host search and return a handle for collect(); up to 4 may be in flight (a server
+        with concurrent requests).  Every rank must submit and collect in the same order."""
+        qn = np.ascontiguousarray(queries, dtype=np.float32)
+        if qn.ndim == 1:
+            qn = qn[None, :]
+        B = qn.shape[0]
+        if self.world == 1:
+            return ("ticket", self.store.submit(qn, k, mask_slot=mask_slot, regime=regime, row_base=self.row_base))
+        if self.exchange is not None and self.store.fused_ok(self.exchange, B, k, regime):
+            self.last_path = "fused"
+            return ("ticket", self.store.submit(qn, k, mask_slot=mask_slot, regime=regime, exchange=self.exchange,
+                                                row_base=self.row_base))
+        return ("done", self.search(qn, k, mask_slot=mask_slot, regime=regime))     # collective path: answered at once
+
+    def collect(self, handle):
+        kind, payload = handle
+        return self.store.collect(payload) if kind == "ticket" else payload
+
     def search(self, queries: np.ndarray, k: int, mask_slot: int = -1, regime: str = "auto"):
         """Host-to-host call: pinned H2D of the queries, shard search, exchange,
         merge, D2H of the final B x k result.  Returns numpy (rows, dists, counts)."""

@@ -66,6 +66,20 @@ def main():
                 ok = ok and good
         if phase == "filter":      # restore for the next batch size
             pass
+    # queries in flight through the fused exchange (submit / collect, 3 in the air): same answers, same order
+    qs = [round_to_bf16(unit_rows(1, dim, 300 + i)) for i in range(12)]
+    want = [full.query(q, k, regime="stream") for q in qs]
+    pend, got = [], []
+    for q in qs:
+        pend.append(searchers["fused"].submit(q, k, regime="stream"))
+        if len(pend) == 3:
+            got.append(searchers["fused"].collect(pend.pop(0)))
+    while pend:
+        got.append(searchers["fused"].collect(pend.pop(0)))
+    good = all(np.array_equal(g[j], w[j]) for g, w in zip(got, want) for j in range(3)) and searchers["fused"].last_path == "fused"
+    if not good:
+        print(f"[rank {rank}] MISMATCH queries in flight through the fused exchange", flush=True)
+    ok = ok and good
     ok = fp32_and_empty_shard_cases(rank, world, local) and ok
     ok = ok and not searchers["fused"].exchange.timed_out()
     latency_report(searchers, rank, dim, k)

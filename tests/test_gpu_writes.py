@@ -147,3 +147,39 @@ def test_async_reader_is_ordered_against_writes():
             assert int(outs[2 * i + 1][0, 0]) == 2000 + i
     finally:
         st.close()
+
+
+def test_queries_in_flight_submit_collect():
+    """rag_store_query_submit / _wait: up to 4 host-buffer queries in the air, results identical to the
+    blocking call, in both regimes, with a filter; a fifth submit is refused; writes in between are seen."""
+    dim, k = 192, 7
+    x = unit_rows(30_000, dim, 8)
+    st = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        st.set_mask(2, (np.arange(30_000) % 3) == 0)
+        qs = [unit_rows(B, dim, 50 + i) for i, B in enumerate((1, 2, 1, 40, 3, 1, 8, 1))]
+        for slot in (-1, 2):
+            want = [st.query(q, k, mask_slot=slot) for q in qs]
+            tickets, got = [], []
+            for q in qs:
+                tickets.append(st.submit(q, k, mask_slot=slot))
+                if len(tickets) == 4:
+                    with pytest.raises(ValueError):
+                        st.submit(q, k)                       # a fifth query in flight is refused
+                    got.append(st.collect(tickets.pop(0)))
+            while tickets:
+                got.append(st.collect(tickets.pop(0)))
+            for g, w in zip(got, want):
+                assert all(np.array_equal(a, b) for a, b in zip(g, w))
+        t = st.submit(x[123], 1)
+        st.upsert(x[123:124] * 0.5, rows=np.array([123]))      # parked write AFTER the submit: not seen by it
+        assert st.collect(t)[0][0, 0] == 123
+        y = unit_rows(1, dim, 999)
+        r = st.upsert(y)
+        t = st.submit(y[0], 1)                                  # submit flushes the parked write first
+        assert st.collect(t)[0][0, 0] == r[0]
+        with pytest.raises(ValueError):
+            st.collect((0, 1, 1))                               # nothing in flight on that ticket
+    finally:
+        st.close()
