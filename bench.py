@@ -438,7 +438,7 @@ def roofline_of(pk, regime_seen, B, rows, dim, dtype, kernel_ms, live_frac=1.0, 
     return out
 
 
-def attach_traffic(roof, rows, dim, dtype, B):
+def attach_traffic(roof, rows, dim, dtype, B, selectivity=None):
     """DRAM traffic of the kernel from the committed ncu captures (profiles/traffic.json), valid only for
     the shard shape it was captured at."""
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -446,7 +446,7 @@ def attach_traffic(roof, rows, dim, dtype, B):
         return
     for ent in json.load(open(tpath)).get("kernels", []):
         if (ent["kernel"] == roof["kernel"] and ent["rows"] == rows and ent["dim"] == dim
-                and ent["dtype"] == dtype and ent["batch"] == B):
+                and ent["dtype"] == dtype and ent["batch"] == B and ent.get("where_selectivity") == selectivity):
             roof["traffic"] = ent["dram_bytes_per_launch"]
             roof["traffic_source"] = ent["source"]
 
@@ -561,7 +561,8 @@ def sharding_desc(world, exchange_path):
     return f"row-wise x{world}, NCCL all-gather of Bxk keys + merge kernel"
 
 
-def measure_batch(env, args, store, searcher, B, k, n_local, pk, mask_slot=-1, K=30, W=3, live_frac=1.0, masks=0, seed=99):
+def measure_batch(env, args, store, searcher, B, k, n_local, pk, mask_slot=-1, K=30, W=3, live_frac=1.0, masks=0, seed=99,
+                  selectivity=None):
     """Device-resident QPS + roofline of one batch size on an existing store."""
     torch = env.torch
     q_dev = torch.from_numpy(gaussian_queries(W + K, B, store.dim, seed=seed)).to(env.dev)
@@ -573,7 +574,7 @@ def measure_batch(env, args, store, searcher, B, k, n_local, pk, mask_slot=-1, K
     out = {"batch": B, "k": k, "value": B / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "regime": regime_seen,
            "steps": K, "warmup": W}
     out["roofline"] = roofline_of(pk, regime_seen, B, n_local, store.dim, store.dtype, kernel_ms, live_frac, masks)
-    attach_traffic(out["roofline"], n_local, store.dim, store.dtype, B)
+    attach_traffic(out["roofline"], n_local, store.dim, store.dtype, B, selectivity)
     return out
 
 
@@ -614,7 +615,7 @@ def other_configs(env, args, rag, ShardedSearcher, pk, which):
                 passing = bucket < pct                                      # where={"bucket": {"$lt": pct}} as a bitmap
                 store.set_mask(slot, passing)
                 r = measure_batch(env, args, store, searcher, 1, 10, n, pk, mask_slot=slot, K=100, W=5,
-                                  live_frac=live * float(passing.mean()), masks=1)
+                                  live_frac=live * float(passing.mean()), masks=1, selectivity=pct / 100.0)
                 r["config"] = (f"BASELINE configs[3]: 10M x 384 {args.dtype}, cosine, top-10, where selectivity {pct} %, "
                                f"5 % tombstones")
                 r["where_selectivity"] = pct / 100.0
@@ -784,7 +785,7 @@ def main():
         timing = "the timed region (the contraction is > 99.8 % of a step)"
     roof = roofline_of(pk, regime_seen, B, n_local, args.dim, args.dtype, kernel_ms, live_frac, 1 if mask_slot >= 0 else 0)
     roof["timing"] = timing
-    attach_traffic(roof, n_local, args.dim, args.dtype, B)
+    attach_traffic(roof, n_local, args.dim, args.dtype, B, args.selectivity or None)
 
     regimes = []
     for xb in [int(v) for v in args.extra_batches.split(",") if v.strip()]:

@@ -346,6 +346,7 @@ int launch_upsert_rows(rag_store* s, const float* d_src, int64_t n, const int64_
 int flush_pending_locked(rag_store* s) {
   PendingWrites& p = s->pending;
   if (p.n == 0) return RAG_OK;
+  NvtxRange nvtx("rag:flush_writes");
   QueryCtx& c = s->admin;
   const size_t row_in = (size_t)s->dim * sizeof(float);
   const size_t vec_b = align_up((size_t)p.n * row_in, 256);
@@ -490,6 +491,7 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
                        int mask_slot, int regime, RowMap rows_map, const SearchOut& out, bool timed,
                        rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor, const float* h_inline) {
   cudaStream_t st = c->stream;
+  NvtxRange nvtx(regime == 2 ? "rag:search:tensor" : (xchg ? "rag:search:stream+exchange" : "rag:search:stream"));
   int rc = c->ensure_events();
   if (rc != RAG_OK) return rc;
   {   // order this stream behind the last write it has not seen yet
@@ -613,9 +615,13 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
   if (refine) {   // merge to scratch keys first (local rows), then re-score the winners exactly
     ma.rows_map = RowMap{}; ma.out_keys = d_merged; ma.out_rows = nullptr; ma.out_dists = nullptr; ma.out_counts = nullptr;
   }
-  CUDA_TRY(launch_merge(ma, st));
+  {
+    NvtxRange nvtx_m("rag:merge");
+    CUDA_TRY(launch_merge(ma, st));
+  }
   launches++;
   if (refine) {
+    NvtxRange nvtx_r("rag:rerank");
     RefineArgs ra{};
     ra.keys = d_merged; ra.B = B; ra.k = k; ra.k_in = k_lists;
     if (rerank) {       // the un-rounded fp32 plane and the un-rounded queries
@@ -808,6 +814,7 @@ static int upsert_impl(rag_store* s, int64_t n, const float* vectors, bool on_de
   if (n < 0) return fail(RAG_EINVAL, "n < 0");
   if (n == 0) return RAG_OK;
   if (!vectors) return fail(RAG_EINVAL, "vectors is NULL");
+  NvtxRange nvtx("rag:upsert");
   WrLock g(&s->lock);
   CUDA_TRY(cudaSetDevice(s->device));
   std::vector<int64_t> dst, claimed;
@@ -938,6 +945,7 @@ int rag_store_delete(rag_store* s, int64_t n, const int64_t* rows) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");
   if (n <= 0) return RAG_OK;
   if (!rows) return fail(RAG_EINVAL, "rows is NULL");
+  NvtxRange nvtx("rag:delete");
   WrLock g(&s->lock);
   CUDA_TRY(cudaSetDevice(s->device));
   int rc = flush_pending_locked(s);      // a parked write to a victim must set its live bit BEFORE it is cleared
@@ -1015,6 +1023,7 @@ int rag_store_set_mask(rag_store* s, int slot, const uint64_t* bits, int64_t nbi
   if (!s) return fail(RAG_EINVAL, "store is NULL");
   if (slot < 0 || slot >= RAG_MAX_MASK_SLOTS) return fail(RAG_EINVAL, "mask slot %d out of range", slot);
   if (nbits < 0 || (nbits > 0 && !bits)) return fail(RAG_EINVAL, "bad mask arguments");
+  NvtxRange nvtx("rag:mask");
   WrLock g(&s->lock);
   CUDA_TRY(cudaSetDevice(s->device));
   const int64_t words64 = (nbits + 63) / 64;
@@ -1052,6 +1061,7 @@ int rag_store_patch_mask(rag_store* s, int slot, int64_t n, const int64_t* rows,
   if (slot < 0 || slot >= RAG_MAX_MASK_SLOTS) return fail(RAG_EINVAL, "mask slot %d out of range", slot);
   if (n <= 0) return RAG_OK;
   if (!rows || !pass) return fail(RAG_EINVAL, "rows/pass is NULL");
+  NvtxRange nvtx("rag:mask");
   WrLock g(&s->lock);
   if (!s->mask_set[slot]) return fail(RAG_EINVAL, "mask slot %d is not set", slot);
   CUDA_TRY(cudaSetDevice(s->device));
@@ -1545,6 +1555,7 @@ int rag_store_query_wait(rag_store* s, int ticket, int64_t* out_rows, float* out
 int rag_merge_keys_dev(int device, int G, int B, int k, const uint64_t* keys_dev, uint64_t* out_keys_dev,
                        int64_t* out_rows_dev, float* out_dists_dev, int32_t* out_counts_dev, void* stream) {
   if (G <= 0 || B <= 0 || k < 1 || k > RAG_MAX_K || !keys_dev) return fail(RAG_EINVAL, "bad merge arguments");
+  NvtxRange nvtx("rag:merge");
   CUDA_TRY(cudaSetDevice(device));
   MergeArgs ma{};
   ma.keys = keys_dev; ma.S = G; ma.B = B; ma.k = k;

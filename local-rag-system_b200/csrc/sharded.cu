@@ -462,6 +462,7 @@ int rag_sharded_query(rag_sharded* s, int B, const float* queries, int k, int ma
                       int64_t* out_rows, float* out_dists, int32_t* out_counts) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");
   if (!out_rows || !out_dists || !out_counts) return fail(RAG_EINVAL, "output pointer is NULL");
+  NvtxRange nvtx("rag:sharded_query");
   RdLock rl(&s->lock);
   rag_store* s0 = s->shard[0];
   int rc = check_query_args(s0, B, queries, k, mask_slot);

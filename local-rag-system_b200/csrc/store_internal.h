@@ -10,6 +10,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/rag_b200.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -29,6 +31,16 @@ int fail(int code, const char* fmt, ...);      // sets the thread-local rag_last
   } while (0)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// NVTX range around a host-side phase (header-only NVTX3: a no-op unless a tool is attached).  Ranges:
+// rag:upsert, rag:flush_writes, rag:delete, rag:mask, rag:search:stream, rag:search:stream+exchange,
+// rag:search:tensor, rag:merge, rag:rerank, rag:sharded_query
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // per-caller scratch: one stream + pinned staging + device scratch
 struct QueryCtx {

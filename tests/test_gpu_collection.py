@@ -149,3 +149,24 @@ def test_persistence_roundtrip_and_chroma_import(tmp_path, golden):
     assert after["ids"] == before["ids"] and after["documents"] == before["documents"]
     assert np.allclose(after["distances"][0], before["distances"][0], atol=1e-7)
     _reset_registry_for_tests()
+
+
+def test_shim_import_on_device(tmp_path, golden):
+    """Drop-in at the reference's own boundary ON THE ENGINE: a subprocess with shim/ first on PYTHONPATH does
+    `import chromadb` and replays the reference's call shapes (tests/shim_on_device_script.py) -- no test double."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "shim"), root]), PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "shim_on_device_script.py"), str(tmp_path / "vs")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    assert out["count"] == 25 and out["engine"] == "DeviceStore" and out["kernel_launches"] > 0 and out["regime"] == "stream"
+    for name, a in out["known"].items():
+        assert a["ok"], (name, a, golden["known"][name])
+    assert out["uris_none"]
+    assert out["count_after_add"] == 26 and out["count_after_delete_where"] == 25 and out["count_after_delete_ids"] == 24
+    assert os.path.exists(tmp_path / "vs" / "rag_b200.sqlite3")
