@@ -81,7 +81,7 @@ def parse():
     ap.add_argument("--tombstones", type=float, default=0.0, help="config 4: delete this fraction of rows first")
     ap.add_argument("--extra-batches", default="1024",
                     help="comma list of further batch sizes measured device-resident on the headline corpus")
-    ap.add_argument("--inflight", type=int, default=2, help="host-buffer queries kept in flight in the e2e pass (1-4)")
+    ap.add_argument("--inflight", type=int, default=3, help="host-buffer queries kept in flight in the e2e pass (1-4)")
     ap.add_argument("--configs", default="2,4,5",
                     help="comma list of the other BASELINE configs to measure under 'regimes' ('' = none)")
     return ap.parse_args()

@@ -436,11 +436,6 @@ bool rag::direct_host_ok(const rag_store* s, int B, int k, int regime) {
          scan_stream_groups(B, s->dtype, s->row_elems, scan_k(s, k)) == 1;
 }
 
-bool rag::inline_query_ok(const rag_store* s, int B, int regime) {
-  static const bool on = !(getenv("RAG_B200_INLINE_QUERY") && atoi(getenv("RAG_B200_INLINE_QUERY")) == 0);
-  return on && B == 1 && regime == 1 && s->dim <= kInlineQueryMax && fused_merge_enabled();
-}
-
 int rag::wait_host_flag(const volatile uint32_t* flag, uint32_t seq, cudaStream_t st) {
   for (uint32_t spins = 1;; ++spins) {
     if (*flag == seq) { std::atomic_thread_fence(std::memory_order_acquire); return RAG_OK; }
@@ -489,7 +484,7 @@ int rag::flush_if_pending(rag_store* s) {
 // shard-local search on device buffers.  Emits keys and/or rows; everything is asynchronous on c->stream.
 int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
                        int mask_slot, int regime, RowMap rows_map, const SearchOut& out, bool timed,
-                       rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor, const float* h_inline) {
+                       rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor) {
   cudaStream_t st = c->stream;
   NvtxRange nvtx(regime == 2 ? "rag:search:tensor" : (xchg ? "rag:search:stream+exchange" : "rag:search:stream"));
   int rc = c->ensure_events();
@@ -568,8 +563,8 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
       if (rc != RAG_OK) return rc;
       sa.done = c->d_tickets;
       sa.queries = nullptr; sa.queries_raw = d_queries_raw;
-      if (h_inline != nullptr && inline_query_ok(s, B, 1)) { sa.inline_host = h_inline; sa.queries_raw = nullptr; }
       if (rerank) { sa.exact = s->d_exact; sa.exact_elems = s->exact_elems; }
+      if (out.query_flag != nullptr) { sa.query_flag = out.query_flag; sa.query_seq = out.query_seq; }
       if (out.done_flag != nullptr && direct_host_ok(s, B, k, 1)) {
         sa.done_flag = out.done_flag; sa.done_seq = out.done_seq;
         if (out.armed) *out.armed = true;
@@ -647,7 +642,7 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
       sa.k = k; sa.k_out = k;
       sa.partial = d_partial;
       sa.done = c->d_tickets;
-      sa.queries = nullptr; sa.queries_raw = d_queries_raw; sa.inline_host = nullptr;
+      sa.queries = nullptr; sa.queries_raw = d_queries_raw;
       sa.round_bf16 = 0;
       sa.q_count = d_redo; sa.q_index = d_redo + 1;
       CUDA_TRY(launch_scan_stream(sa, s->sm_count, st, &launches));
@@ -775,7 +770,11 @@ int rag_store_destroy(rag_store* s) {
   }
   for (QueryCtx* c : s->pool_free) { c->destroy(); delete c; }
   for (auto& kv : s->dev_ctx) { kv.second->destroy(); delete kv.second; }
-  if (s->pipe) { if (s->pipe->stream) cudaStreamDestroy(s->pipe->stream); delete s->pipe; }
+  if (s->pipe) {
+    if (s->pipe->stream) cudaStreamDestroy(s->pipe->stream);
+    if (s->pipe->copy_stream) cudaStreamDestroy(s->pipe->copy_stream);
+    delete s->pipe;
+  }
   s->admin.destroy();
   if (s->ev_write) cudaEventDestroy(s->ev_write);
   if (s->pending.ev_h2d) cudaEventDestroy(s->pending.ev_h2d);
@@ -1145,14 +1144,8 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
     so.counts = reinterpret_cast<int32_t*>(d + in_b + rows_b + dist_b);
     unsigned char* scratch = d + in_b + rows_b + dist_b + cnt_b;
 
-    const float* q_host = queries + (size_t)b0 * s->dim;
-    // (a lone blocking query gains nothing from riding in the launch parameters -- 0.330 vs 0.319 ms on a 1.25M x 768
-    // shard: every CTA then reads it through the constant cache -- so only queries in flight do, rag_store_query_submit)
-    const bool inl = false;
-    if (!inl) {
-      memcpy(c->h_pin, q_host, (size_t)Bc * s->dim * sizeof(float));
-      CUDA_TRY(cudaMemcpyAsync(d_in, c->h_pin, (size_t)Bc * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    }
+    memcpy(c->h_pin, queries + (size_t)b0 * s->dim, (size_t)Bc * s->dim * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(d_in, c->h_pin, (size_t)Bc * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     bool armed = false;
     if (direct_host_ok(s, Bc, k, regime)) {
       // small stream-regime batch: the kernel writes the result straight into the pinned block (mapped host
@@ -1164,8 +1157,7 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
       so.done_seq = ++c->signal_seq ? c->signal_seq : ++c->signal_seq;
       so.armed = &armed;
     }
-    rc = search_device(s, c, scratch, Bc, d_in, k, mask_slot, regime, RowMap{}, so, true, nullptr, 0u, flags == RAG_QUERY_FORCE_TENSOR,
-                       inl ? q_host : nullptr);
+    rc = search_device(s, c, scratch, Bc, d_in, k, mask_slot, regime, RowMap{}, so, true, nullptr, 0u, flags == RAG_QUERY_FORCE_TENSOR);
     if (rc != RAG_OK) return rc;
     regime_used = s->last_regime.load();     // the regime that actually ran (an fp32 store may have fallen back)
     if (armed) {
@@ -1388,11 +1380,8 @@ int rag_store_query_fused(rag_store* s, rag_exchange* x, int B, const float* que
   rc = c->ensure_dev(io_b + search_scratch_bytes(s, B, k, grid_x));
   if (rc != RAG_OK) return rc;
   unsigned char* d = c->d_buf;
-  const bool inl = false;                  // see rag_store_query
-  if (!inl) {
-    memcpy(c->h_pin, queries, (size_t)B * s->dim * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(d, c->h_pin, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  }
+  memcpy(c->h_pin, queries, (size_t)B * s->dim * sizeof(float));
+  CUDA_TRY(cudaMemcpyAsync(d, c->h_pin, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   SearchOut so{};
   so.rows = reinterpret_cast<int64_t*>(d + in_b);
   so.dists = reinterpret_cast<float*>(d + in_b + rows_b);
@@ -1407,7 +1396,7 @@ int rag_store_query_fused(rag_store* s, rag_exchange* x, int B, const float* que
     so.armed = &armed;
   }
   rc = search_device(s, c, d + io_b, B, reinterpret_cast<const float*>(d), k, mask_slot, 1, RowMap{row_base, 0u, 1u}, so,
-                     false, x, epoch, false, inl ? queries : nullptr);
+                     false, x, epoch, false);
   if (rc != RAG_OK) return rc;
   if (armed) {
     rc = wait_host_flag(so.done_flag, so.done_seq, c->stream);
@@ -1433,9 +1422,10 @@ static int pipeline_of(rag_store* s, Pipeline** out) {
   Pipeline* p = new (std::nothrow) Pipeline();
   if (!p) return fail(RAG_ENOMEM, "out of host memory");
   cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete p; return fail(RAG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { if (p->stream) cudaStreamDestroy(p->stream); delete p; return fail(RAG_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
   int rc = dev_ctx_for(s, p->stream, &p->ctx);
-  if (rc != RAG_OK) { cudaStreamDestroy(p->stream); delete p; return rc; }
+  if (rc != RAG_OK) { cudaStreamDestroy(p->stream); cudaStreamDestroy(p->copy_stream); delete p; return rc; }
   s->pipe = p;
   *out = p;
   return RAG_OK;
@@ -1496,15 +1486,31 @@ int rag_store_query_submit(rag_store* s, rag_exchange* x, int B, const float* qu
   const int grid_x = scan_stream_grid_x(s->sm_count, s->rows);
   rc = c->ensure_dev(search_scratch_bytes(s, B, k, grid_x));
   if (rc != RAG_OK) return rc;
-  const bool inl = inline_query_ok(s, B, regime);
-  if (!inl) {
+  // The queries of a small stream-regime batch go down on the COPY stream, followed by an arrival flag the kernel
+  // waits for: no operation then sits between two searches on the pipeline stream, which would undo their
+  // programmatic overlap (1.25M x 768 shard, 2 in flight: 0.287 ms per query; plain copy on the pipeline stream 0.304;
+  // query in the launch parameters 0.290 -- that variant also made a lone blocking query slower and was removed).
+  static const bool side_on = !(getenv("RAG_B200_INFLIGHT_QUERY") && atoi(getenv("RAG_B200_INFLIGHT_QUERY")) == 0);
+  const bool fused_stream = regime == 1 && direct_host_ok(s, B, k, regime);
+  const bool side = side_on && fused_stream;
+  SearchOut so{};
+  if (side) {
+    uint32_t* h_flag = reinterpret_cast<uint32_t*>(ps.h + io_b - 128);       // pinned source of the flag value
+    uint32_t* d_flag = reinterpret_cast<uint32_t*>(ps.d + io_b - 128);
+    ps.qseq = ++ps.qseq ? ps.qseq : ++ps.qseq;
+    memcpy(ps.h, queries, (size_t)B * s->dim * sizeof(float));
+    *h_flag = ps.qseq;
+    CUDA_TRY(cudaMemcpyAsync(ps.d, ps.h, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, p->copy_stream));
+    CUDA_TRY(cudaMemcpyAsync(d_flag, h_flag, sizeof(uint32_t), cudaMemcpyHostToDevice, p->copy_stream));   // stream-ordered behind the queries
+    so.query_flag = d_flag;
+    so.query_seq = ps.qseq;
+  } else {
     memcpy(ps.h, queries, (size_t)B * s->dim * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(ps.d, ps.h, (size_t)B * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
-  SearchOut so{};
   bool armed = false;
   unsigned char* ob = ps.d;
-  if (direct_host_ok(s, B, k, regime)) {
+  if (fused_stream) {
     ob = ps.h;
     so.done_flag = reinterpret_cast<uint32_t*>(ps.h + io_b - 256);
     so.done_seq = ++ps.seq ? ps.seq : ++ps.seq;
@@ -1514,7 +1520,7 @@ int rag_store_query_submit(rag_store* s, rag_exchange* x, int B, const float* qu
   so.dists = reinterpret_cast<float*>(ob + ps.in_b + ps.rows_b);
   so.counts = reinterpret_cast<int32_t*>(ob + ps.in_b + ps.rows_b + ps.dist_b);
   rc = search_device(s, c, c->d_buf, B, reinterpret_cast<const float*>(ps.d), k, mask_slot, regime, RowMap{row_base, 0u, 1u}, so,
-                     false, x, epoch, flags == RAG_QUERY_FORCE_TENSOR, inl ? queries : nullptr);
+                     false, x, epoch, flags == RAG_QUERY_FORCE_TENSOR);
   if (rc != RAG_OK) return rc;
   if (!armed) {
     CUDA_TRY(cudaMemcpyAsync(ps.h + ps.in_b, ps.d + ps.in_b, ps.rows_b + ps.dist_b + ps.cnt_b, cudaMemcpyDeviceToHost, c->stream));

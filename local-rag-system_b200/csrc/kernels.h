@@ -24,12 +24,6 @@ struct ScanArgs {
   int64_t filter_words;     // words available in `filter`
   const float* queries;     // [B][row_elems] prepared fp32, or nullptr when queries_raw is given
   const float* queries_raw; // [B][dim] raw fp32: the kernel normalises / rounds them itself (saves a launch)
-  // HOST pointer (consumed by the launcher, never dereferenced on the device): a single query of dim <=
-  // kInlineQueryMax rides in the kernel's launch parameters instead of being copied to the device first.  No
-  // copy operation then sits between two searches on a stream, so host-buffer queries IN FLIGHT keep their
-  // programmatic overlap (1.25M x 768 shard, 2 in flight: 0.285 vs 0.300 ms per query).  A lone blocking query is
-  // better off with the copy (0.319 vs 0.330 ms): every CTA reads an inline query through the constant cache.
-  const float* inline_host;
   int dim, normalise, round_bf16;
   int B;
   int k;                    // list length kept per query during the scan
@@ -60,6 +54,12 @@ struct ScanArgs {
   int xchg_rank, xchg_world;
   uint32_t xchg_epoch;      // >= 1, identical on every rank, +1 per call (parity picks the buffer half)
   int64_t xchg_slot_keys;   // keys per (parity, rank) slot; B * k must fit
+  // Queries that arrive on ANOTHER stream (queries in flight, rag_store_query_submit): the host copies them to
+  // `queries_raw` on a copy stream and then copies `query_seq` to *query_flag; the kernel -- launched with no stream
+  // dependency on those copies, so that no operation sits between two searches and their programmatic overlap
+  // survives -- waits for the flag before it reads the queries (it is normally there long before).  nullptr = off.
+  const uint32_t* query_flag;
+  uint32_t query_seq;
   // Completion signal for host-resident outputs (nullptr = off; only with one query group per launch):
   // out_rows / out_dists / out_counts may point into MAPPED PINNED host memory -- the last CTA then writes the
   // B x k result straight over PCIe and finally stores done_seq to *done_flag (release, system scope), which
@@ -84,9 +84,6 @@ constexpr size_t kXchgKeysOff = kXchgFlagBytes + 64 * sizeof(uint32_t);
 inline size_t xchg_buffer_bytes(int world, int64_t slot_keys) {
   return kXchgKeysOff + 2ull * world * static_cast<size_t>(slot_keys) * sizeof(uint64_t);
 }
-// 896 floats + ScanArgs stay inside the classic 4 KB of launch parameters; beyond it the launch takes the
-// large-parameter path, measured ~14 us slower per launch (1.25M x 768 shard, one blocking query: 0.336 vs 0.322 ms)
-constexpr int kInlineQueryMax = 896;
 // picks QB (queries per pass) and the kernel instantiation; returns cudaError_t
 cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st, int* launches);
 // grid_x the launcher will use for this problem (so the caller can size `partial`)

@@ -22,9 +22,6 @@
 //   R x NJ independent 16-byte streaming loads (no L1 allocation) before the
 //   first FMA, so 16 resident warps/SM keep ~96 KB/SM in flight.
 #include <stdlib.h>
-#include <string.h>
-
-#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -99,15 +96,8 @@ __device__ __forceinline__ float chunk_acc(float acc, const uint4& v, const floa
 // every lane busy; the 32/LPR sub-warps of a warp work on different rows).  NJ > 0: a row is
 // exactly NJ x LPR chunks (fully unrolled, no guards); NJ == 0: any row length (LPR = 32).
 // R row slots in flight per warp, i.e. R x 32/LPR rows.
-struct InlineQuery { float v[kInlineQueryMax]; };
-static_assert(sizeof(ScanArgs) + sizeof(InlineQuery) <= 4096, "the inline query must keep the launch parameters within 4 KB");
-struct NoInlineQuery {};
-
-// INLQ: the (single) raw query arrives in the launch parameters (`iq`), not in global memory.
-template <bool BF16, int QB, int NJ, int R, bool L2, int LPR, bool INLQ>
-__global__ void __launch_bounds__(kScanThreads, 2)
-scan_stream_kernel(const ScanArgs a, const std::conditional_t<INLQ, InlineQuery, NoInlineQuery> iq) {
-  static_assert(!INLQ || QB == 1, "only a single query rides in the launch parameters");
+template <bool BF16, int QB, int NJ, int R, bool L2, int LPR>
+__global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const ScanArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int V = R * QB;
   constexpr int G = 32 / LPR;                      // rows per slot
@@ -136,17 +126,23 @@ scan_stream_kernel(const ScanArgs a, const std::conditional_t<INLQ, InlineQuery,
   float* q_s = reinterpret_cast<float*>(smem_raw);
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(QB) * row_elems * sizeof(float));
 
+  if (a.query_flag != nullptr) {       // the queries come down on a copy stream: wait until they have landed
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = global_timer_ns();
+      while (ld_acquire_sys_u32(a.query_flag) != a.query_seq) {
+        if (global_timer_ns() - t0 > 5000000000ull) __trap();      // 5 s: the copy failed; surface it as a launch error
+      }
+    }
+    __syncthreads();
+  }
+
   // ---- stage queries (fp32, chunk-major so that lanes read consecutive float4) ----
   // With queries_raw the CTA prepares them itself exactly as prep_queries_kernel would (same
   // lane-strided summation order -> bit-identical values in both regimes): cosine stores scale
   // by 1/|q|, bf16 stores round to bf16.
   __shared__ float s_scale[QB];
-  // element e of raw query `bs` (parameter space is indexed directly: taking its address would copy it to local memory)
-  auto raw_q = [&](int bs, int e) -> float {
-    if constexpr (INLQ) { (void)bs; return iq.v[e]; }
-    else return a.queries_raw[static_cast<size_t>(bs) * a.dim + e];
-  };
-  const bool have_raw = INLQ || a.queries_raw != nullptr;
+  auto raw_q = [&](int bs, int e) -> float { return a.queries_raw[static_cast<size_t>(bs) * a.dim + e]; };
+  const bool have_raw = a.queries_raw != nullptr;
   if (have_raw) {
     if (warp < QB) {
       const int b = b0 + warp;
@@ -669,8 +665,8 @@ size_t scan_total_smem(int QB, int row_elems, int k, int grid_x, int* merge_cap)
   return need;
 }
 
-template <typename Kern, typename IQ>
-cudaError_t launch_pdl(Kern kern, const ScanArgs& a, const IQ& iq, dim3 grid, size_t smem, cudaStream_t st) {
+template <typename Kern>
+cudaError_t launch_pdl(Kern kern, const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -686,21 +682,13 @@ cudaError_t launch_pdl(Kern kern, const ScanArgs& a, const IQ& iq, dim3 grid, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, a, iq);
+  return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 template <bool BF16, int QB, int NJ, int R, int LPR>
 cudaError_t launch_one(const ScanArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  if constexpr (QB == 1) {
-    if (a.inline_host != nullptr) {          // the query rides in the launch parameters
-      InlineQuery iq;
-      memcpy(iq.v, a.inline_host, static_cast<size_t>(a.dim) * sizeof(float));
-      if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR, true>, a, iq, grid, smem, st);
-      return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR, true>, a, iq, grid, smem, st);
-    }
-  }
-  if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR, false>, a, NoInlineQuery{}, grid, smem, st);
-  return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR, false>, a, NoInlineQuery{}, grid, smem, st);
+  if (a.l2) return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, true, LPR>, a, grid, smem, st);
+  return launch_pdl(scan_stream_kernel<BF16, QB, NJ, R, false, LPR>, a, grid, smem, st);
 }
 
 template <bool BF16, int QB>
@@ -748,7 +736,6 @@ int scan_stream_max_qb(int dtype, int row_elems, int k) {
 
 cudaError_t launch_scan_stream(const ScanArgs& a, int sm_count, cudaStream_t st, int* launches) {
   if (a.B <= 0 || a.k <= 0) return cudaErrorInvalidValue;
-  if (a.inline_host != nullptr && (a.B != 1 || a.dim > kInlineQueryMax || a.q_index != nullptr)) return cudaErrorInvalidValue;
   const int max_qb = scan_stream_max_qb(a.dtype, a.row_elems, a.k);
   int QB = 1;
   while (QB < a.B && QB < max_qb) QB <<= 1;

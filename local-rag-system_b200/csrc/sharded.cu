@@ -117,15 +117,14 @@ int run_fused_shard(rag_sharded* s, int g, const SearchOut& so) {
   rc = c->ensure_dev(in_b + out_b + search_scratch_bytes(st, j.B, j.k, grid_x));
   if (rc != RAG_OK) return rc;
   unsigned char* d = c->d_buf;
-  const bool inl = false;                                // blocking call: the copy is cheaper than launch parameters (see rag_store_query)
-  if (!inl) CUDA_TRY(cudaMemcpyAsync(d, s->h_q, (size_t)j.B * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(d, s->h_q, (size_t)j.B * s->dim * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   SearchOut o = so;
   if (!o.rows) {              // shards other than 0 still need somewhere to put the (identical) result
     o.rows = reinterpret_cast<int64_t*>(d + in_b);
     o.dists = nullptr; o.counts = nullptr;
   }
   return search_device(st, c, d + in_b + out_b, j.B, reinterpret_cast<const float*>(d), j.k, j.mask_slot, 1, map_of(s, g), o,
-                       g == 0, s->xchg[g], j.epoch, false, inl ? reinterpret_cast<const float*>(s->h_q) : nullptr);
+                       g == 0, s->xchg[g], j.epoch, false);
 }
 
 void worker_main(rag_sharded* s, int g) {

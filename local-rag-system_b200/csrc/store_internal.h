@@ -87,6 +87,7 @@ struct PipeSlot {
   size_t bytes = 0;
   cudaEvent_t ev = nullptr;        // behind the slot's last device-to-host copy (when the flag path is not used)
   uint32_t seq = 0;
+  uint32_t qseq = 0;               // arrival flag value of the slot's queries (flag word: last 4 bytes of the 256-byte tail of `d`)
   bool busy = false, armed = false;
   int B = 0, k = 0;
   size_t in_b = 0, rows_b = 0, dist_b = 0, cnt_b = 0;
@@ -94,6 +95,7 @@ struct PipeSlot {
 struct Pipeline {
   static constexpr int kSlots = 4;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // carries the queries (and their arrival flags) of in-flight requests
   QueryCtx* ctx = nullptr;         // registered with the store like any asynchronous reader (scratch, write ordering)
   PipeSlot slot[kSlots];
   uint32_t next = 0;
@@ -105,6 +107,9 @@ struct SearchOut {
   int64_t* rows = nullptr;
   float* dists = nullptr;
   int32_t* counts = nullptr;
+  // optional arrival flag of queries copied on another stream (see ScanArgs::query_flag)
+  const uint32_t* query_flag = nullptr;
+  uint32_t query_seq = 0;
   // optional completion flag in mapped pinned host memory (rows / dists / counts then point there too): if the
   // launch can raise it (fused stream regime, one query group) search_device sets *armed and the caller polls
   // the flag with wait_host_flag() instead of copying the result back and synchronising the stream
@@ -184,12 +189,9 @@ namespace rag {
 // read lock held by the caller.  Orders the context's stream behind the last write, runs the regime's
 // kernels asynchronously on c->stream.  `scratch` must hold search_scratch_bytes().
 size_t search_scratch_bytes(const rag_store* s, int B, int k, int grid_x);
-// h_inline (may be NULL): the same queries in HOST memory; where inline_query_ok() holds the single query then
-// rides in the launch parameters and d_queries_raw is not read (the caller need not have copied it down).
 int search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B, const float* d_queries_raw, int k,
                   int mask_slot, int regime, RowMap rows_map, const SearchOut& out, bool timed,
-                  rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor, const float* h_inline = nullptr);
-bool inline_query_ok(const rag_store* s, int B, int regime);
+                  rag_exchange* xchg, uint32_t xchg_epoch, bool forced_tensor);
 int choose_regime(const rag_store* s, int B, int k, int flags);
 int batch_limit(const rag_store* s, int k);
 int check_query_args(const rag_store* s, int B, const void* q, int k, int mask_slot);
