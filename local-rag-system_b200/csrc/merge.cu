@@ -112,6 +112,66 @@ __global__ void __launch_bounds__(kMergeThreads) merge_small_kernel(const MergeA
   if (lane == 0 && a.out_counts) a.out_counts[b] = cnt;
 }
 
+// Medium fan-in (33 <= S <= 512 lists, k <= 128: the tensor regime's per-CTA lists when the batch has few query
+// tiles, e.g. S = 148 at B <= 128): one CTA per query, thread t owns lists t and t + 256 and keeps each list's head
+// and next key in registers; k rounds of block-wide minimum (two barriers each, no memory latency unless the same
+// list wins twice in a row).  The general kernel above walks the lists warp by warp with cooperative insertions:
+// 34.8 us for S = 148, k = 16, B = 32 (ncu, profiles/r02_launches_f32_b32.csv) -- 8 % of that step.
+__global__ void __launch_bounds__(kMergeThreads) merge_kway_kernel(const MergeArgs a) {
+  __shared__ uint64_t wmin[kMergeWarps];
+  __shared__ int total;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int k = a.k;
+  uint64_t cur[2], nxt[2];
+  int pos[2];
+  const uint64_t* lst[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int s = threadIdx.x + u * kMergeThreads;
+    lst[u] = a.keys + (static_cast<size_t>(s < a.S ? s : 0) * a.B + b) * k;
+    pos[u] = 0;
+    cur[u] = (s < a.S) ? __ldcg(lst[u]) : kEmptyKey;
+    nxt[u] = (s < a.S && k > 1) ? __ldcg(lst[u] + 1) : kEmptyKey;
+  }
+  if (threadIdx.x == 0) total = 0;
+  for (int r = 0; r < k; ++r) {
+    uint64_t m = cur[0] < cur[1] ? cur[0] : cur[1];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const uint64_t o = shfl_u64(m, lane ^ off);
+      m = o < m ? o : m;
+    }
+    if (lane == 0) wmin[warp] = m;
+    __syncthreads();
+    uint64_t w = wmin[0];
+#pragma unroll
+    for (int i = 1; i < kMergeWarps; ++i) w = wmin[i] < w ? wmin[i] : w;
+    if (threadIdx.x == 0) {
+      uint64_t key = w;
+      const bool valid = key != kEmptyKey;
+      if (valid) { key = key_to_global(a.rows_map, key); total++; }
+      const size_t o = static_cast<size_t>(b) * k + r;
+      if (a.out_keys) a.out_keys[o] = key;
+      if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
+      if (a.out_dists) a.out_dists[o] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+    }
+    if (w != kEmptyKey) {                // keys are unique: exactly one list head equals w
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (cur[u] == w) {
+          cur[u] = nxt[u];
+          pos[u]++;
+          nxt[u] = (pos[u] + 1 < k) ? __ldcg(lst[u] + pos[u] + 1) : kEmptyKey;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && a.out_counts) a.out_counts[b] = total;
+}
+
 // ---- exact re-scoring of the approximate winners (tensor regime) --------------------------------
 // The tensor kernel ranks l2 by |q|^2 + |x|^2 - 2 q.x (cancellation error grows with the norms) and,
 // for fp32 stores, contracts bf16 hi/lo splits (~1e-6 absolute error on a unit-norm dot product).
@@ -202,6 +262,10 @@ cudaError_t launch_merge(const MergeArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.k <= 0 || a.S <= 0) return cudaErrorInvalidValue;
   if (a.S <= 32 && a.k <= 64) {
     merge_small_kernel<<<(a.B + kMergeWarps - 1) / kMergeWarps, kMergeThreads, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  if (a.S <= 2 * kMergeThreads && a.k <= 128) {
+    merge_kway_kernel<<<a.B, kMergeThreads, 0, st>>>(a);
     return cudaGetLastError();
   }
   const size_t smem = static_cast<size_t>(kMergeWarps) * next_pow2(a.k) * sizeof(uint64_t);

@@ -311,6 +311,7 @@ TENSOR_CASES = [
     ("cosine", 6000, 768, 200, 100),      # CTA pairs, 768-wide A operand (2 accumulators), heaps in shared memory
     ("l2", 3000, 768, 30, 100),           # one query tile, 768-d, k = 100: the heap block does not fit -> local memory
     ("ip", 5000, 512, 260, 120),          # three query tiles (one idle), k = 120
+    ("cosine", 4000, 128, 20, 200),       # k > 128: heaps in local memory, the general merge kernel
 ]
 
 
