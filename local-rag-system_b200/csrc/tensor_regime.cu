@@ -259,6 +259,7 @@ __device__ unsigned long long g_tensor_stats[8];
 
 struct Args {
   int lists_in_smem;             // 16 < k <= 128: the per-thread heaps live in shared memory behind the barriers
+  uint32_t q_early, q_late_mask; // quantile bound: refreshed every 8th tile for the first q_early tiles, then when (it & mask) == 1
   int stats;                     // 1: count into g_tensor_stats (debug; costs a few atomics per slow-path tile)
   const __nv_bfloat16* q_bf16;   // [n_mtiles*128][row_elems] prepared queries, zero rows beyond B
   const float* q_norm2;          // [n_mtiles*128]
@@ -569,7 +570,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         tau = fminf(tau, tau_g);
       }
       if constexpr (KL > 16) {
-        if (use_q && refresh) {                      // T = max over the CTAs' q-th best (all must have one)
+        // the quantile bound costs cpm global loads per THREAD whose latency nothing hides: every 8th tile only while
+        // the bound still moves fast (the first 512 tiles of this CTA), every 128th afterwards.  Refreshing it every
+        // 8th tile throughout was the single largest cost of k > 16: 25M x 384 l2 k = 100 23.1-24.9 -> 19.2-20.0 ms,
+        // 10M x 768 cosine k = 100 16.5-17.3 -> 14.4 ms (the ncu source page had it as a 5.6 % stall on one VIMNMX3,
+        // profiles/r02_c5_k100_source_top.txt line 946 -- but every such stall also held a buffer of the pair)
+        if (use_q && refresh && (it < a.q_early || (it & a.q_late_mask) == 1u)) {      // T = max over the CTAs' q-th best (all must have one)
           uint32_t worst = 0u;
           for (int c = 0; c < a.cpm; ++c) {
             uint32_t v;
@@ -1088,6 +1094,10 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   a.nbuf = (L.nb == kNB && ((width + 15) / 16) * 8 + 4 * kNB <= kTmemCols) ? 4 : 2;
   if (const char* e = getenv("RAG_B200_TENSOR_NBUF")) { if (atoi(e) == 2) a.nbuf = 2; }
   a.dense = p.dense;
+  a.q_early = 512u;
+  a.q_late_mask = 127u;
+  if (const char* ev = getenv("RAG_B200_TENSOR_QEARLY")) a.q_early = static_cast<uint32_t>(atoi(ev));
+  if (const char* ev = getenv("RAG_B200_TENSOR_QLATE")) a.q_late_mask = (1u << atoi(ev)) - 1u;      // log2 of the late interval (>= 3)
   static const int stats_on = (getenv("RAG_B200_TENSOR_STATS") && atoi(getenv("RAG_B200_TENSOR_STATS")) == 1) ? 1 : 0;
   a.stats = stats_on;
   a.prefetch = 0;
