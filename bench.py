@@ -13,8 +13,10 @@ the scan kernel (peer memory over NVLink) or an NCCL all-gather + merge kernel.
 One JSON line on rank 0 (keys per the driver contract):
   value     QPS with the query batch already in HBM (device-timed, CUDA events, max over
             ranks); back-to-back launches overlap by programmatic dependent launch (value_note)
-  e2e       the same metric through the public host-buffer call: pinned H2D of the queries,
-            search, D2H of the B x k result, inside the timed region
+  e2e       the same metric through the public host-buffer API with 3 queries in flight (submit /
+            collect: a server with concurrent requests): every step's queries go pinned host ->
+            device and its B x k result comes back to the host inside the timed region; the
+            one-blocking-call-per-step numbers sit beside it (sequential_value, p50_ms)
   roofline  scan kernel: algorithmic bytes (rows x row_bytes) / its CUDA-event time vs
             MEASURED_PEAKS.json hbm_gbs
   verified  the engine's answers for this very corpus against a chunked fp32 brute force over
