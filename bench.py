@@ -415,10 +415,13 @@ def kernel_time(store, q_host, k, mask_slot, regime, n=5):
     return statistics.mean(kms), regime_seen
 
 
-def roofline_of(pk, regime_seen, B, rows, dim, dtype, kernel_ms, live_frac=1.0, masks=0, bitmap_rows=None):
+def roofline_of(pk, regime_seen, B, rows, dim, dtype, kernel_ms, live_frac=1.0, masks=0, bitmap_rows=None, shadow=None):
     """The bound that applies: HBM (bytes the kernel is designed to touch: live & passing rows + bitmaps) or the
-    tensor pipe (2 B N D).  For the tensor kernel the larger of the two fractions is reported."""
+    tensor pipe (2 B N D).  For the tensor kernel the larger of the two fractions is reported.  fp32 stores in the
+    tensor regime stream their bf16 shadow (`shadow`: "hi" = 2 bytes per element, "hilo" = 4)."""
     row_bytes = dim * (2 if dtype == "bf16" else 4)
+    if dtype == "f32" and regime_seen == "tensor" and shadow == "hi":
+        row_bytes = dim * 2
     alg_bytes = float(rows) * live_frac * row_bytes + (bitmap_rows if bitmap_rows is not None else rows) / 8.0 * (1 + masks)
     hbm = alg_bytes / (kernel_ms / 1e3) / 1e9
     kern = "gemm_topk_kernel" if regime_seen == "tensor" else "scan_stream_kernel"
@@ -433,10 +436,13 @@ def roofline_of(pk, regime_seen, B, rows, dim, dtype, kernel_ms, live_frac=1.0, 
                    "frac": tf / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"] + " burst",
                    "frac_of_sustained_peak": tf / pk["bf16_tflops_sustained"], "kernel": kern, "kernel_ms": kernel_ms,
                    "algorithmic_flops": flops}
-            if dtype == "f32":
+            if dtype == "f32" and shadow != "hi":
                 # fp32 rows are contracted as bf16 hi/lo pairs: 3 MMAs per algorithmic one
                 out["executed_tflops"] = 3.0 * tf
                 out["executed_frac"] = 3.0 * tf / pk["bf16_tflops"]
+    if dtype == "f32" and regime_seen == "tensor":
+        out["streams"] = f"bf16 shadow of the fp32 rows ({shadow}): {row_bytes} B per row"
+        out["frac_on_fp32_row_bytes"] = float(rows) * live_frac * dim * 4 / (kernel_ms / 1e3) / 1e9 / pk["hbm_gbs"]
     return out
 
 
@@ -575,7 +581,14 @@ def measure_batch(env, args, store, searcher, B, k, n_local, pk, mask_slot=-1, K
         kernel_ms = ms        # the contraction is > 99.8 % of a step (profiles/): the timed region itself, at its clocks
     out = {"batch": B, "k": k, "value": B / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "regime": regime_seen,
            "steps": K, "warmup": W}
-    out["roofline"] = roofline_of(pk, regime_seen, B, n_local, store.dim, store.dtype, kernel_ms, live_frac, masks)
+    shadow = None
+    if store.dtype == "f32" and regime_seen == "tensor":
+        ti = store.f32_tensor_info()
+        shadow = ti["shadow"]
+        out["f32_tensor"] = {"shadow": shadow, "queries": ti["queries"], "exact_reruns": ti["reruns"],
+                             "note": "bf16 shadow contracted on the tensor cores, survivors re-ranked from the fp32 rows, "
+                                     "each query certified by the guard or re-run on the exact stream kernel"}
+    out["roofline"] = roofline_of(pk, regime_seen, B, n_local, store.dim, store.dtype, kernel_ms, live_frac, masks, shadow=shadow)
     attach_traffic(out["roofline"], n_local, store.dim, store.dtype, B, selectivity)
     return out
 
@@ -605,6 +618,13 @@ def other_configs(env, args, rag, ShardedSearcher, pk, which):
                     r["build"] = binfo
                 out.append(r)
         with_store(1_000_000, 384, "f32", "cosine", cfg2)
+
+        def cfg2_wide(store, searcher, binfo):      # not a BASELINE config: fp32 rows of the headline width (dim > 384)
+            for B in (32, 1024):
+                r = measure_batch(env, args, store, searcher, B, 10, 1_000_000, pk, K=50 if B < 1024 else 20, W=5)
+                r["config"] = "beyond BASELINE configs[1]: 1M x 768 fp32, cosine, top-10 (fp32 rows wider than 384)"
+                out.append(r)
+        with_store(1_000_000, 768, "f32", "cosine", cfg2_wide)
     if 4 in which and env.world == 1:
         def cfg4(store, searcher, binfo):
             n = 10_000_000

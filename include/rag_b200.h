@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 2
+#define RAG_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -284,6 +284,23 @@ RAG_API int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int*
 RAG_API int rag_debug_tensor_stats(uint64_t* out8, int reset);
 /* device time (ms, CUDA events on the admin stream) of the upsert kernel of the last rag_store_upsert_dev */
 RAG_API float rag_store_last_upsert_ms(const rag_store* s);
+
+/* -- fp32 stores in the tensor regime (large query batches; replaces the same collection.query call,
+ * api/app.py:544-549, on a store created with dtype f32) -------------------------------------------
+ * The tensor cores contract a bf16 SHADOW of the fp32 rows; the survivors are re-ranked exactly from the
+ * fp32 rows and a guard certifies, per query, that no row outside the survivors can belong to the top k
+ * (queries it cannot certify are re-run on the exact stream kernel inside the same call).  Two shadows:
+ *   RAG_F32_SHADOW_HI    bf16(x) only: half the bytes and a third of the tensor work; rounding error ~1e-3 |q||x|,
+ *                        covered by keeping 64-128 survivors.  Any dim % 8 == 0 up to 768.  Default.
+ *   RAG_F32_SHADOW_HILO  [hi | lo] split precision, error ~1e-6 |q||x|; dim % 16 == 0 up to 384.  A store moves
+ *                        here by itself when the hi-only guard keeps failing (> 1/8 of the queries).
+ * rag_store_set_f32_shadow pins a kind (RAG_F32_SHADOW_AUTO = back to the policy); _info reports the kind in
+ * force and how many tensor-regime queries were served / had to be re-run exactly since the store was created. */
+#define RAG_F32_SHADOW_AUTO 0
+#define RAG_F32_SHADOW_HI 1
+#define RAG_F32_SHADOW_HILO 2
+RAG_API int rag_store_set_f32_shadow(rag_store* s, int kind);
+RAG_API int rag_store_f32_tensor_info(const rag_store* s, int* shadow_kind, int64_t* queries, int64_t* reruns);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,8 @@ MAX_K = 1024
 MAX_MASK_SLOTS = 16
 EXCHANGE_HANDLE_BYTES = 64
 STORE_NO_RERANK = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
+F32_SHADOW_AUTO, F32_SHADOW_HI, F32_SHADOW_HILO = 0, 1, 2
 
 _p = C.c_void_p
 _i64p = C.POINTER(C.c_int64)
@@ -97,6 +98,8 @@ SIGNATURES = {
     "rag_debug_tensor_stats": (C.c_int, [_u64p, C.c_int]),
     "rag_store_last_upsert_ms": (C.c_float, [_p]),
     "rag_store_last_query_info": (C.c_int, [_p, _f32p, _i32p, _i32p]),
+    "rag_store_set_f32_shadow": (C.c_int, [_p, C.c_int]),
+    "rag_store_f32_tensor_info": (C.c_int, [_p, _i32p, _i64p, _i64p]),
 }
 
 _lib = None

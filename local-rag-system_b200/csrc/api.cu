@@ -86,10 +86,11 @@ void QueryCtx::destroy() {
   if (h_pin) cudaFreeHost(h_pin);
   if (d_buf) cudaFree(d_buf);
   if (d_tickets) cudaFree(d_tickets);
+  if (h_redo) cudaFreeHost(h_redo);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (ev_done) cudaEventDestroy(ev_done);
-  stream = nullptr; h_pin = nullptr; d_buf = nullptr; d_tickets = nullptr; ev0 = ev1 = ev_done = nullptr;
+  stream = nullptr; h_pin = nullptr; d_buf = nullptr; d_tickets = nullptr; h_redo = nullptr; ev0 = ev1 = ev_done = nullptr;
   h_bytes = d_bytes = 0;
 }
 
@@ -335,6 +336,8 @@ int launch_upsert_rows(rag_store* s, const float* d_src, int64_t n, const int64_
   a.exact = s->d_exact;
   a.exact_elems = s->exact_elems;
   a.shadow = s->d_shadow;
+  a.shadow_kind = s->shadow_kind;
+  a.lo_max2 = s->d_max_norm2 + 2;
   a.rows = d_rows;
   a.row0 = row0;
   CUDA_TRY(launch_upsert(a, s->admin.stream));
@@ -387,21 +390,45 @@ void fill_empty(int B, int k, int64_t* out_rows, float* out_dists, int32_t* out_
   if (out_counts) for (int b = 0; b < B; ++b) out_counts[b] = 0;
 }
 
-// fp32 store about to be searched by the tensor regime: make sure its bf16 hi/lo shadow exists
+// fp32 store about to be searched by the tensor regime: make sure its bf16 shadow (of kind s->shadow_kind) exists
 // (read lock held: no writer is active; concurrent readers serialise on shadow_mu)
 int ensure_shadow(rag_store* s, cudaStream_t st) {
   std::lock_guard<std::mutex> g(s->shadow_mu);
   if (s->d_shadow) return RAG_OK;
   __nv_bfloat16* sh = nullptr;
-  const size_t bytes = (size_t)s->capacity * 2 * s->row_elems * sizeof(__nv_bfloat16);
+  const size_t bytes = (size_t)s->capacity * (s->shadow_kind == kShadowHiLo ? 2 : 1) * s->row_elems * sizeof(__nv_bfloat16);
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&sh), bytes);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RAG_ENOMEM, "cudaMalloc of %zu bytes for the split-precision shadow failed: %s", bytes, cudaGetErrorString(e)); }
-  e = launch_split_rows(reinterpret_cast<const float*>(s->d_vectors), s->row_elems, 0, s->rows, sh, st);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(RAG_ENOMEM, "cudaMalloc of %zu bytes for the bf16 shadow failed: %s", bytes, cudaGetErrorString(e)); }
+  e = cudaMemsetAsync(s->d_max_norm2 + 2, 0, sizeof(float), st);       // the bound restarts from the rows held now
+  if (e == cudaSuccess)
+    e = launch_split_rows(reinterpret_cast<const float*>(s->d_vectors), s->row_elems, 0, s->rows, sh, s->shadow_kind,
+                          s->d_max_norm2 + 2, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(sh); return fail(RAG_ECUDA, "building the split-precision shadow failed: %s", cudaGetErrorString(e)); }
+  if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(sh); return fail(RAG_ECUDA, "building the bf16 shadow failed: %s", cudaGetErrorString(e)); }
   s->d_shadow = sh;
   s->launches++;
   return RAG_OK;
+}
+
+// statistics of the fp32 tensor regime: the re-run count of a context's previous batch has come back by now (it was
+// copied behind that batch; a context runs one batch at a time).  Feeds the totals and the hi-only policy window.
+void harvest_redo(rag_store* s, QueryCtx* c) {
+  if (c->redo_batch <= 0 || c->h_redo == nullptr) return;
+  const int seen = *reinterpret_cast<volatile int*>(c->h_redo);
+  const int redo = seen < 0 ? 0 : (seen > c->redo_batch ? c->redo_batch : seen);
+  s->f32_tensor_queries += c->redo_batch;
+  s->f32_tensor_reruns += redo;
+  s->last_batch_reruns.store(redo, std::memory_order_relaxed);
+  if (c->redo_kind == kShadowHi && !s->shadow_pinned) {
+    const int64_t q = (s->hi_window_queries += c->redo_batch);
+    const int64_t r = (s->hi_window_reruns += redo);
+    // more than 1/8 of >= 64 queries could not be certified: the rows are packed closer than the bf16 filter can tell
+    // apart; the hi/lo split (error 1e-6 instead of 1e-3) serves such a store better.  Decided per window of 4096.
+    if (q >= 64 && r * 8 > q && tensor::supported(s->dtype, s->row_elems, 1, s->space, 0, kShadowHiLo))
+      s->want_shadow_kind.store(kShadowHiLo, std::memory_order_release);
+    if (q >= 4096) { s->hi_window_queries = 0; s->hi_window_reruns = 0; }
+  }
+  c->redo_batch = 0;
 }
 
 // scratch of one search: prepared queries | per-CTA partial lists [grid_x][B][k_scan] | redo list |
@@ -418,7 +445,10 @@ ScratchLayout scratch_layout(const rag_store* s, int B, int k, int grid_x) {
   L.off_redo = off; off += align_up((size_t)(B + 1) * sizeof(int), 256);      // redo count + list (split-precision tensor regime)
   L.off_qexact = off; off += align_up((size_t)B * std::max(s->exact_elems, 4) * sizeof(float), 256);
   L.off_merged = off; off += align_up((size_t)B * ks * sizeof(uint64_t), 256);
-  L.off_tensor = off; off += tensor::scratch_bytes(s->dtype, s->row_elems, B, k, s->sm_count, s->exact_elems ? 1 : 0);
+  // (fp32 stores: whichever shadow kind the store has or may move to)
+  L.off_tensor = off;
+  off += std::max(tensor::scratch_bytes(s->dtype, s->row_elems, B, k, s->sm_count, s->exact_elems ? 1 : 0, kShadowHi),
+                  tensor::scratch_bytes(s->dtype, s->row_elems, B, k, s->sm_count, s->exact_elems ? 1 : 0, kShadowHiLo));
   L.total = off;
   return L;
 }
@@ -465,7 +495,7 @@ size_t rag::search_scratch_bytes(const rag_store* s, int B, int k, int grid_x) {
 // Decide the kernel regime for a batch.
 int rag::choose_regime(const rag_store* s, int B, int k, int flags) {
   if (flags == RAG_QUERY_FORCE_STREAM) return 1;
-  const bool tensor_ok = tensor::supported(s->dtype, s->row_elems, k, s->space, s->exact_elems ? 1 : 0);
+  const bool tensor_ok = tensor::supported(s->dtype, s->row_elems, k, s->space, s->exact_elems ? 1 : 0, s->shadow_kind);
   if (flags == RAG_QUERY_FORCE_TENSOR) return tensor_ok ? 2 : -1;
   if (!tensor_ok) return 1;
   // the stream kernel reads the corpus once per group of <= 8 queries; the tensor kernel
@@ -475,9 +505,21 @@ int rag::choose_regime(const rag_store* s, int B, int k, int flags) {
 }
 
 int rag::flush_if_pending(rag_store* s) {
-  if (s->pending_n.load(std::memory_order_acquire) == 0) return RAG_OK;
+  const int want = s->want_shadow_kind.load(std::memory_order_acquire);
+  const bool switch_shadow = want != 0 && want != s->shadow_kind;
+  if (s->pending_n.load(std::memory_order_acquire) == 0 && !switch_shadow) return RAG_OK;
   WrLock g(&s->lock);
   CUDA_TRY(cudaSetDevice(s->device));
+  if (switch_shadow && want != s->shadow_kind) {
+    // like a write: searches in flight may still read the old shadow; the next tensor-regime search rebuilds it
+    int rc = writer_wait_for_readers(s);
+    if (rc != RAG_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s->admin.stream));
+    if (s->d_shadow) { cudaFree(s->d_shadow); s->d_shadow = nullptr; }
+    s->shadow_kind = want;
+    rc = writer_publish(s);
+    if (rc != RAG_OK) return rc;
+  }
   return flush_pending_locked(s);
 }
 
@@ -517,8 +559,9 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
   int S = 0;
   tensor::Result tres{};
   if (regime == 2 && s->dtype == RAG_DTYPE_F32) {
-    // the split-precision regime needs the hi/lo shadow (as many bytes again as the rows).  If the device
-    // cannot hold it, an AUTO query is still answered -- exactly, by the stream kernel, just slower.
+    // the tensor regime contracts a bf16 shadow of the rows (half as many bytes again, or as many for the hi/lo
+    // split).  If the device cannot hold it, an AUTO query is still answered -- exactly, by the stream kernel.
+    harvest_redo(s, c);
     const int rcs = ensure_shadow(s, st);
     if (rcs == RAG_ENOMEM && !forced_tensor) regime = 1;
     else if (rcs != RAG_OK) return rcs;
@@ -538,7 +581,7 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
   if (regime == 2) {
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     tensor::Problem p{};
-    p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.norms2 = s->d_norms2; p.min_norm2 = s->d_max_norm2 + 1; p.n_rows = s->rows; p.row_elems = s->row_elems;
+    p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.shadow_kind = (s->dtype == RAG_DTYPE_F32) ? s->shadow_kind : kShadowNone; p.norms2 = s->d_norms2; p.min_norm2 = s->d_max_norm2 + 1; p.n_rows = s->rows; p.row_elems = s->row_elems;
     p.dim = s->dim; p.dtype = s->dtype; p.space = s->space;
     p.live = s->d_live; p.filter = filter; p.filter_words = fwords;
     p.dense = (filter == nullptr && s->live == s->rows) ? 1 : 0;
@@ -602,7 +645,7 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
     tres.q_exact = d_qexact;
   }
   // ---- generic tail: merge the S lists per query; re-score the winners where ranking was approximate ----
-  const bool split = (regime == 2 && s->dtype == RAG_DTYPE_F32);
+  const bool split = (regime == 2 && s->dtype == RAG_DTYPE_F32);       // contracted through a bf16 shadow (either kind)
   const bool refine = rerank || (regime == 2 && (s->space == RAG_SPACE_L2 || split));
   MergeArgs ma{};
   ma.keys = merge_src; ma.S = S; ma.B = B; ma.k = k_lists; ma.rows_map = rows_map;
@@ -629,11 +672,18 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
     if (split) {
       CUDA_TRY(cudaMemsetAsync(d_redo, 0, sizeof(int), st));
       ra.guard_rel = 1.2e-4f; ra.q_norm2 = tres.q_norm2; ra.x_max_norm2 = s->d_max_norm2;
+      ra.q_lo_norm2 = tres.q_lo_norm2; ra.x_lo_max2 = s->d_max_norm2 + 2;      // hi-only shadow: the bf16 rounding it ignores
       ra.redo_count = d_redo; ra.redo_list = d_redo + 1;
     }
     CUDA_TRY(launch_refine(ra, st));
     launches++;
     if (split) {
+      // statistics: how many queries the guard sends to the re-run (read when this context searches again)
+      if (c->h_redo == nullptr && cudaMallocHost(reinterpret_cast<void**>(&c->h_redo), 64) != cudaSuccess) { (void)cudaGetLastError(); c->h_redo = nullptr; }
+      if (c->h_redo != nullptr) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_redo, d_redo, sizeof(int), cudaMemcpyDeviceToHost, st));
+        c->redo_batch = B; c->redo_kind = s->shadow_kind;
+      }
       // queries whose top-k the approximate ranking could not certify are re-run on the exact fp32
       // stream kernel; the launch covers the worst case and exits at once when the list is empty
       rc = c->ensure_tickets();
@@ -645,6 +695,13 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
       sa.queries = nullptr; sa.queries_raw = d_queries_raw;
       sa.round_bf16 = 0;
       sa.q_count = d_redo; sa.q_index = d_redo + 1;
+      // The launch covers the worst case (every query fails): grid_x x ceil(B / 8) CTAs that exit at once when their
+      // group holds no failed query -- 38k CTAs = 46 us at B = 1024 for nothing.  While the guard certifies everything
+      // (the last harvested batch had no re-run) a large batch gets an eighth of the CTAs per group: the empty launch
+      // costs ~6 us, and should queries fail after all, >= 8 failing groups still fill the machine (fewer run at a
+      // fraction of the HBM rate, once: the count that comes back restores the full grid for the next batch).
+      if (scan_stream_groups(B, s->dtype, s->row_elems, k) > 8 && s->last_batch_reruns.load(std::memory_order_relaxed) == 0)
+        sa.grid_x = std::max(1, grid_x / 8);
       CUDA_TRY(launch_scan_stream(sa, s->sm_count, st, &launches));
     }
   }
@@ -741,9 +798,13 @@ int rag_store_create_ex(int dim, int dtype, int space, int device, int64_t capac
   if (e == cudaSuccess)
     e = cudaMallocHost(reinterpret_cast<void**>(&s->pending.h),
                        (size_t)PendingWrites::kMaxRows * ((size_t)dim * sizeof(float) + sizeof(int64_t)) + 1024);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_max_norm2), 2 * sizeof(float));
+  if (dtype == RAG_DTYPE_F32) {
+    s->shadow_kind = tensor::default_shadow_kind(s->row_elems);
+    s->shadow_pinned = getenv("RAG_B200_F32_SHADOW") != nullptr;
+  }
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_max_norm2), 4 * sizeof(float));
   if (e == cudaSuccess) {
-    const float init[2] = {0.0f, __builtin_inff()};      // [0] running max, [1] running min of |stored row|^2
+    const float init[4] = {0.0f, __builtin_inff(), 0.0f, 0.0f};      // [0] running max, [1] running min of |stored row|^2, [2] max |x - bf16(x)|^2
     e = cudaMemcpy(s->d_max_norm2, init, sizeof(init), cudaMemcpyHostToDevice);
   }
   if (e != cudaSuccess) { (void)cudaGetLastError(); rag_store_destroy(s); return fail(RAG_ENOMEM, "store set-up failed: %s", cudaGetErrorString(e)); }
@@ -1171,6 +1232,7 @@ int rag_store_query(rag_store* s, int B, const float* queries, int k, int mask_s
     memcpy(out_rows + (size_t)b0 * k, c->h_pin + in_b, (size_t)Bc * k * sizeof(int64_t));
     memcpy(out_dists + (size_t)b0 * k, c->h_pin + in_b + rows_b, (size_t)Bc * k * sizeof(float));
     memcpy(out_counts + b0, c->h_pin + in_b + rows_b + dist_b, (size_t)Bc * sizeof(int32_t));
+    harvest_redo(s, c);            // fp32 tensor regime: the guard's re-run count came back with the result
     float ms = 0.0f;
     if (armed) {
       // the flag is raised a moment before the kernel (and the event behind it) completes: leave the timing to
@@ -1580,6 +1642,33 @@ int rag_debug_tensor_stats(uint64_t* out8, int reset) {
 }
 
 float rag_store_last_upsert_ms(const rag_store* s) { return s ? s->last_upsert_ms : 0.0f; }
+
+int rag_store_f32_tensor_info(const rag_store* s, int* shadow_kind, int64_t* queries, int64_t* reruns) {
+  if (!s) return fail(RAG_EINVAL, "store is NULL");
+  if (shadow_kind) {
+    const int want = s->want_shadow_kind.load(std::memory_order_acquire);
+    *shadow_kind = (s->dtype == RAG_DTYPE_F32) ? (want ? want : s->shadow_kind) : 0;
+  }
+  if (queries) *queries = s->f32_tensor_queries.load();
+  if (reruns) *reruns = s->f32_tensor_reruns.load();
+  return RAG_OK;
+}
+
+int rag_store_set_f32_shadow(rag_store* s, int kind) {
+  if (!s) return fail(RAG_EINVAL, "store is NULL");
+  if (s->dtype != RAG_DTYPE_F32) return fail(RAG_EINVAL, "only fp32 stores have a bf16 shadow");
+  if (kind != RAG_F32_SHADOW_AUTO && kind != RAG_F32_SHADOW_HI && kind != RAG_F32_SHADOW_HILO)
+    return fail(RAG_EINVAL, "unknown shadow kind %d", kind);
+  int k = kind;
+  if (kind == RAG_F32_SHADOW_AUTO) k = tensor::default_shadow_kind(s->row_elems);
+  else if (!tensor::supported(s->dtype, s->row_elems, 1, s->space, 0, kind))
+    return fail(RAG_EINVAL, "the tensor regime cannot take a %d-element fp32 row through shadow kind %d", s->row_elems, kind);
+  s->shadow_pinned.store(kind != RAG_F32_SHADOW_AUTO);
+  s->hi_window_queries = 0; s->hi_window_reruns = 0;
+  if (k == 0) return RAG_OK;
+  s->want_shadow_kind.store(k, std::memory_order_release);
+  return flush_if_pending(s);
+}
 
 int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");

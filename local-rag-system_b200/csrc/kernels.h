@@ -118,9 +118,14 @@ struct RefineArgs {
   // approximate distance is not at least 2*guard_eps beyond the exact k-th distance, a row outside
   // the list could belong to the top k: the query index is appended to redo_list (count in
   // redo_count) and re-run on the exact fp32 stream kernel.
-  float guard_rel;          // |approx - exact| <= guard_rel * |q| * max|x| (x 2 for l2)
+  float guard_rel;          // |approx - exact| <= guard_rel * |q| * max|x| (x 2 for l2) ...
   const float* q_norm2;     // [B]
   const float* x_max_norm2; // [1]
+  // ... plus, when the rows were contracted as bf16(x) with bf16(q) only (hi-only shadow, nullptr otherwise), the
+  // rounding that contraction ignores:  |q.x - qh.xh| <= |q - qh| |x| + |qh| |x - xh|   (Cauchy-Schwarz), with
+  // |q - qh| known per query and |x - xh| bounded by its maximum over the store
+  const float* q_lo_norm2;  // [B] |q - bf16(q)|^2
+  const float* x_lo_max2;   // [1] max over the store of |x - bf16(x)|^2
   int* redo_count;
   int* redo_list;
   RowMap rows_map;
@@ -146,13 +151,17 @@ struct UpsertArgs {
   // optional un-rounded fp32 plane of a bf16 store (exact re-ranking): [capacity][exact_elems]; nullptr when absent
   float* exact;
   int exact_elems;
-  // optional split-precision shadow of an fp32 store for the tensor regime: row r is
-  // [hi(row_elems) | lo(row_elems)] bf16 with x = hi + lo + O(2^-17 |x|); nullptr when absent
+  // optional bf16 shadow of an fp32 store for the tensor regime (nullptr when absent), by shadow_kind:
+  //   kShadowHiLo  row r = [hi(row_elems) | lo(row_elems)] with x = hi + lo + O(2^-17 |x|)   (split precision)
+  //   kShadowHi    row r = hi(row_elems) = bf16(x) only                                      (bf16 filter + exact re-rank)
   __nv_bfloat16* shadow;
+  int shadow_kind;
+  float* lo_max2;           // [1] running maximum of |x - bf16(x)|^2 over the rows written while a shadow exists, or nullptr
 };
-// (re)build the shadow of rows [row0, row0 + n) from the stored fp32 rows
+constexpr int kShadowNone = 0, kShadowHi = 1, kShadowHiLo = 2;
+// (re)build the shadow of rows [row0, row0 + n) from the stored fp32 rows; lo_max2 as in UpsertArgs
 cudaError_t launch_split_rows(const float* vectors, int row_elems, int64_t row0, int64_t n,
-                              __nv_bfloat16* shadow, cudaStream_t st);
+                              __nv_bfloat16* shadow, int shadow_kind, float* lo_max2, cudaStream_t st);
 cudaError_t launch_upsert(const UpsertArgs& a, cudaStream_t st);
 
 // K7: clear live bits
@@ -169,6 +178,7 @@ struct PrepArgs {
   int exact_elems;
   __nv_bfloat16* q_bf16;    // [Bpad][row_elems * (split ? 2 : 1)] or nullptr (rows >= B zero-filled by caller)
   float* q_norm2;           // [B] or nullptr
+  float* q_lo_norm2;        // [B] |x - bf16(x)|^2 of the prepared (un-rounded) query, or nullptr
   // optional initialisation of the scan kernel's merge state (done here to save launches)
   uint64_t* init_keys;      // filled with kEmptyKey (init_keys_n entries) or nullptr
   int64_t init_keys_n;

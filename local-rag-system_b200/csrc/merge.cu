@@ -222,7 +222,13 @@ __global__ void __launch_bounds__(kMergeThreads) refine_kernel(const RefineArgs 
     if (worst_in != kEmptyKey && keys[k - 1] != kEmptyKey) {
       const float a_max = key_dist(worst_in);
       const float d_k = key_dist(keys[k - 1]);
-      const float eps = a.guard_rel * sqrtf(a.q_norm2[b] * a.x_max_norm2[0]) * (a.l2 ? 2.0f : 1.0f);
+      const float qn = sqrtf(a.q_norm2[b]), xn = sqrtf(a.x_max_norm2[0]);
+      float eps = a.guard_rel * qn * xn;
+      if (a.q_lo_norm2 != nullptr) {      // hi-only contraction: what rounding q and x to bf16 can have moved (kernels.h)
+        const float ql = sqrtf(a.q_lo_norm2[b]), xl = sqrtf(a.x_lo_max2[0]);
+        eps += 1.01f * (ql * xn + (qn + ql) * xl);
+      }
+      if (a.l2) eps *= 2.0f;
       if (!(a_max - d_k > 2.0f * eps)) a.redo_list[atomicAdd(a.redo_count, 1)] = b;
     }
   }

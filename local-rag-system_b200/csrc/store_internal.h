@@ -57,6 +57,11 @@ struct QueryCtx {
   uint32_t signal_seq = 0;                       // last value handed to a kernel as its completion signal
   unsigned int* d_tickets = nullptr;             // kMaxTickets zeroed counters, self-resetting (scan kernel)
   static constexpr int kMaxTickets = 4096;
+  // fp32 tensor regime: how many queries of this context's last such batch the guard sent to the exact re-run
+  // (copied back behind the batch, read lazily: statistics for rag_store_f32_tensor_info and the shadow policy)
+  int* h_redo = nullptr;                         // pinned [1]
+  int redo_batch = 0;                            // queries of the batch h_redo belongs to (0 = nothing outstanding)
+  int redo_kind = 0;                             // shadow kind that batch ran on
 
   int ensure_tickets();
   int ensure_host(size_t bytes);
@@ -146,11 +151,21 @@ struct rag_store {
   void* d_vectors = nullptr;
   float* d_exact = nullptr;               // bf16 stores: un-rounded fp32 rows (normalised for cosine) for the exact re-ranking
   float* d_norms2 = nullptr;
-  float* d_max_norm2 = nullptr;           // [2] largest / smallest |stored row|^2 ever written
+  float* d_max_norm2 = nullptr;           // [4]: [0] largest, [1] smallest |stored row|^2 ever written; [2] largest |x - bf16(x)|^2
+                                          // over the rows written while a shadow existed (reset when one is built)
   uint32_t* d_live = nullptr;
-  // fp32 stores, tensor regime: bf16 [capacity][hi(row_elems) | lo(row_elems)] split of the rows, built on
-  // the first large-batch query, kept in step by upsert, dropped (and rebuilt lazily) when the store grows
+  // fp32 stores, tensor regime: bf16 shadow of the rows -- [capacity][hi(row_elems)] (kShadowHi: bf16 filter + exact
+  // re-ranking + guard) or [capacity][hi | lo] (kShadowHiLo: split precision) -- built on the first large-batch
+  // query, kept in step by upsert, dropped (and rebuilt lazily) when the store grows or the kind changes.
+  // A store starts with tensor::default_shadow_kind(); when the guard of the hi-only filter sends more than 1/8 of
+  // the queries to the exact re-run (rows packed closer than bf16 can tell apart) it moves to the hi/lo split for good.
   __nv_bfloat16* d_shadow = nullptr;
+  int shadow_kind = 0;                    // kind of d_shadow / of the shadow to build (write lock or shadow_mu)
+  std::atomic<int> want_shadow_kind{0};   // != shadow_kind: switch before the next search (flush_if_pending)
+  std::atomic<bool> shadow_pinned{false}; // kind fixed by rag_store_set_f32_shadow / RAG_B200_F32_SHADOW: no policy
+  std::atomic<int64_t> f32_tensor_queries{0}, f32_tensor_reruns{0};      // lifetime totals (all kinds)
+  std::atomic<int64_t> hi_window_queries{0}, hi_window_reruns{0};        // current policy window (hi-only batches)
+  std::atomic<int> last_batch_reruns{1};  // re-runs of the most recent harvested batch (sizes the next re-run launch)
   std::mutex shadow_mu;
   uint32_t* d_masks[RAG_MAX_MASK_SLOTS] = {};     // each capacity / 32 words, zero beyond mask_words
   int64_t mask_words[RAG_MAX_MASK_SLOTS] = {};
@@ -199,7 +214,8 @@ int check_query_args(const rag_store* s, int B, const void* q, int k, int mask_s
 bool direct_host_ok(const rag_store* s, int B, int k, int regime);
 // spin on a completion flag in mapped pinned memory; falls back to the stream's status to surface errors
 int wait_host_flag(const volatile uint32_t* flag, uint32_t seq, cudaStream_t st);
-// pending small writes -> device (takes the write lock itself when there is something to do)
+// pending small writes -> device, pending change of the fp32 shadow kind (takes the write lock itself when there
+// is something to do)
 int flush_if_pending(rag_store* s);
 int dev_ctx_for(rag_store* s, void* stream, QueryCtx** out);
 // list length the scan keeps for a request of k hits (k + slack with the exact re-ranking)

@@ -25,7 +25,7 @@ __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(_
 
 // ---- K1: normalise / convert on upsert -------------------------------------------------------------
 // Roofline: HBM.  Algorithmic bytes per row = dim * 4 read + row_bytes written (+ dim * 4 for the fp32
-// re-ranking plane of a bf16 store, + 2 * row_bytes for the hi/lo shadow of an fp32 store once it exists).
+// re-ranking plane of a bf16 store, + row_bytes / 2 or row_bytes for the hi / hi-lo shadow of an fp32 store once it exists).
 //
 // Vector path (dim % 4 == 0, dim <= 2048): ONE pass, one warp per row.  Lane l holds the 8 consecutive
 // elements 8 * (l + 32 j) .. + 7 of the row for j < NJ in registers (two 16-byte streaming loads each, a warp
@@ -51,6 +51,12 @@ __device__ __forceinline__ void track_norm_bounds(float* max_norm2, float stored
     atomicMin(reinterpret_cast<unsigned int*>(max_norm2 + 1), bits);
 }
 
+__device__ __forceinline__ void track_max(float* slot, float v) {      // non-negative floats order like their bit patterns
+  if (slot == nullptr) return;
+  const unsigned int bits = __float_as_uint(v);
+  if (bits > *reinterpret_cast<volatile unsigned int*>(slot)) atomicMax(reinterpret_cast<unsigned int*>(slot), bits);
+}
+
 template <int NJ>
 __global__ void __launch_bounds__(kThreads) upsert_kernel(const UpsertArgs a) {
   const int lane = threadIdx.x & 31;
@@ -74,6 +80,7 @@ __global__ void __launch_bounds__(kThreads) upsert_kernel(const UpsertArgs a) {
   ss = warp_sum(ss);
   const float scale = a.normalise ? (ss > 0.0f ? rsqrtf(ss) : 0.0f) : 1.0f;
   float stored_ss = 0.0f;
+  float lo_ss = 0.0f;                                  // |x - bf16(x)|^2 (fp32 stores with a shadow)
   const int re4 = a.row_elems >> 2;                    // destination row in float4 (fp32) units
 #pragma unroll
   for (int j = 0; j < NJ; ++j) {
@@ -106,25 +113,33 @@ __global__ void __launch_bounds__(kThreads) upsert_kernel(const UpsertArgs a) {
       float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.vectors) + row * a.row_elems);
       if (c < re4) dst[c] = lo;
       if (c + 1 < re4) dst[c + 1] = hi;
-      if (a.shadow != nullptr) {                       // keep the split-precision shadow in step with the row
-        __nv_bfloat16* sh = a.shadow + row * 2 * a.row_elems;
+      if (a.shadow != nullptr) {                       // keep the bf16 shadow in step with the row
+        const bool hilo = (a.shadow_kind == kShadowHiLo);
+        __nv_bfloat16* sh = a.shadow + row * (hilo ? 2 : 1) * a.row_elems;
         const float4 q[2] = {lo, hi};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (c + h >= re4) continue;
-          uint2 wh, wl;
+          uint2 wh;
           wh.x = pack_bf16x2(q[h].x, q[h].y); wh.y = pack_bf16x2(q[h].z, q[h].w);
-          wl.x = pack_bf16x2(q[h].x - bf16_lo(wh.x), q[h].y - bf16_hi(wh.x));
-          wl.y = pack_bf16x2(q[h].z - bf16_lo(wh.y), q[h].w - bf16_hi(wh.y));
+          const float r0 = q[h].x - bf16_lo(wh.x), r1 = q[h].y - bf16_hi(wh.x);
+          const float r2 = q[h].z - bf16_lo(wh.y), r3 = q[h].w - bf16_hi(wh.y);
+          lo_ss = fmaf(r0, r0, lo_ss); lo_ss = fmaf(r1, r1, lo_ss); lo_ss = fmaf(r2, r2, lo_ss); lo_ss = fmaf(r3, r3, lo_ss);
           *reinterpret_cast<uint2*>(sh + 4 * (c + h)) = wh;
-          *reinterpret_cast<uint2*>(sh + a.row_elems + 4 * (c + h)) = wl;
+          if (hilo) {
+            uint2 wl;
+            wl.x = pack_bf16x2(r0, r1); wl.y = pack_bf16x2(r2, r3);
+            *reinterpret_cast<uint2*>(sh + a.row_elems + 4 * (c + h)) = wl;
+          }
         }
       }
     }
   }
   stored_ss = warp_sum(stored_ss);
+  if (a.shadow != nullptr && a.lo_max2 != nullptr) lo_ss = warp_sum(lo_ss);
   if (lane == 0) {
     track_norm_bounds(a.max_norm2, stored_ss);
+    if (a.shadow != nullptr) track_max(a.lo_max2, lo_ss);
     a.norms2[row] = stored_ss;
     atomicOr(a.live + (row >> 5), 1u << (row & 31));
   }
@@ -142,6 +157,7 @@ __global__ void __launch_bounds__(kThreads) upsert_generic_kernel(const UpsertAr
   ss = warp_sum(ss);
   const float scale = a.normalise ? (ss > 0.0f ? rsqrtf(ss) : 0.0f) : 1.0f;
   float stored_ss = 0.0f;
+  float lo_ss = 0.0f;
   if (a.dtype == 1) {
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.vectors) + row * a.row_elems;
     for (int e = lane; e < a.row_elems; e += 32) {
@@ -158,35 +174,54 @@ __global__ void __launch_bounds__(kThreads) upsert_generic_kernel(const UpsertAr
       float x = (e < a.dim) ? src[e] * scale : 0.0f;
       stored_ss = fmaf(x, x, stored_ss);
       dst[e] = x;
-      if (a.shadow) {                  // keep the split-precision shadow in step with the row
+      if (a.shadow) {                  // keep the bf16 shadow in step with the row
         const __nv_bfloat16 h = __float2bfloat16_rn(x);
-        a.shadow[row * 2 * a.row_elems + e] = h;
-        a.shadow[row * 2 * a.row_elems + a.row_elems + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+        const float r = x - __bfloat162float(h);
+        lo_ss = fmaf(r, r, lo_ss);
+        if (a.shadow_kind == kShadowHiLo) {
+          a.shadow[row * 2 * a.row_elems + e] = h;
+          a.shadow[row * 2 * a.row_elems + a.row_elems + e] = __float2bfloat16_rn(r);
+        } else {
+          a.shadow[row * a.row_elems + e] = h;
+        }
       }
     }
   }
   stored_ss = warp_sum(stored_ss);
+  lo_ss = warp_sum(lo_ss);
   if (lane == 0) {
     track_norm_bounds(a.max_norm2, stored_ss);
+    if (a.shadow != nullptr) track_max(a.lo_max2, lo_ss);
     a.norms2[row] = stored_ss;
     atomicOr(a.live + (row >> 5), 1u << (row & 31));
   }
 }
 
-// x = hi + lo + O(2^-18 |x|): two bf16 planes that let the tensor cores contract fp32 rows
+// bf16 shadow of fp32 rows for the tensor regime, one warp per row.  kShadowHiLo: x = hi + lo + O(2^-18 |x|), two
+// bf16 planes side by side that let the tensor cores contract fp32 rows; kShadowHi: bf16(x) only (half the bytes; the
+// contraction is then a FILTER whose survivors are re-ranked exactly).  Either way the largest |x - bf16(x)|^2 of a
+// row is tracked: with the norms it bounds what the hi-only contraction can miss (refine_kernel's guard).
 __global__ void __launch_bounds__(kThreads) split_rows_kernel(const float* vectors, int row_elems, int64_t row0,
-                                                             int64_t n, __nv_bfloat16* shadow) {
-  const int64_t total = n * row_elems;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / row_elems;
-    const int e = static_cast<int>(i - r * row_elems);
-    const float x = vectors[(row0 + r) * row_elems + e];
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    __nv_bfloat16* dst = shadow + (row0 + r) * 2 * row_elems;
-    dst[e] = h;
-    dst[row_elems + e] = __float2bfloat16_rn(x - __bfloat162float(h));
+                                                             int64_t n, __nv_bfloat16* shadow, int kind, float* lo_max2) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * kWarpsPerCta;
+  float worst = 0.0f;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5); r < n; r += warps) {
+    const float* src = vectors + (row0 + r) * row_elems;
+    __nv_bfloat16* dst = shadow + (row0 + r) * (kind == kShadowHiLo ? 2 : 1) * row_elems;
+    float lo_ss = 0.0f;
+    for (int e = lane; e < row_elems; e += 32) {
+      const float x = src[e];
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      const float rem = x - __bfloat162float(h);
+      lo_ss = fmaf(rem, rem, lo_ss);
+      dst[e] = h;
+      if (kind == kShadowHiLo) dst[row_elems + e] = __float2bfloat16_rn(rem);
+    }
+    lo_ss = warp_sum(lo_ss);
+    worst = fmaxf(worst, lo_ss);
   }
+  if (lane == 0 && worst > 0.0f) track_max(lo_max2, worst);
 }
 
 __global__ void clear_live_kernel(uint32_t* live, const int64_t* rows, int64_t n) {
@@ -219,12 +254,13 @@ __global__ void __launch_bounds__(kThreads) prep_queries_kernel(const PrepArgs a
   for (int e = lane; e < a.dim; e += 32) { float x = src[e]; ss = fmaf(x, x, ss); }
   ss = warp_sum(ss);
   const float scale = a.normalise ? (ss > 0.0f ? rsqrtf(ss) : 0.0f) : 1.0f;
-  float n2 = 0.0f;
+  float n2 = 0.0f, lo2 = 0.0f;
   for (int e = lane; e < a.row_elems; e += 32) {
     float x = (e < a.dim) ? src[e] * scale : 0.0f;
     if (a.q_exact != nullptr && e < a.exact_elems) a.q_exact[static_cast<size_t>(b) * a.exact_elems + e] = x;
     if (a.round_bf16) x = round_bf16(x);
     n2 = fmaf(x, x, n2);
+    { const float rem = x - round_bf16(x); lo2 = fmaf(rem, rem, lo2); }
     a.q_f32[static_cast<size_t>(b) * a.row_elems + e] = x;
     if (a.q_bf16) {
       if (a.split) {
@@ -239,6 +275,10 @@ __global__ void __launch_bounds__(kThreads) prep_queries_kernel(const PrepArgs a
   }
   n2 = warp_sum(n2);
   if (lane == 0 && a.q_norm2) a.q_norm2[b] = n2;
+  if (a.q_lo_norm2) {
+    lo2 = warp_sum(lo2);
+    if (lane == 0) a.q_lo_norm2[b] = lo2;
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) fetch_kernel(const void* vectors, int dtype, int dim, int row_elems,
@@ -280,12 +320,11 @@ cudaError_t launch_patch_mask(uint32_t* mask, const int64_t* rows_dev, const uns
 }
 
 cudaError_t launch_split_rows(const float* vectors, int row_elems, int64_t row0, int64_t n, __nv_bfloat16* shadow,
-                              cudaStream_t st) {
+                              int shadow_kind, float* lo_max2, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const int64_t total = n * row_elems;
-  int64_t ctas = (total + kThreads - 1) / kThreads;
+  int64_t ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
   if (ctas > 148 * 16) ctas = 148 * 16;
-  split_rows_kernel<<<static_cast<unsigned>(ctas), kThreads, 0, st>>>(vectors, row_elems, row0, n, shadow);
+  split_rows_kernel<<<static_cast<unsigned>(ctas), kThreads, 0, st>>>(vectors, row_elems, row0, n, shadow, shadow_kind, lo_max2);
   return cudaGetLastError();
 }
 

@@ -33,6 +33,7 @@
 #include <cuda_bf16.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -926,7 +927,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
   int n_mtiles, cpm, cl, mode, nb;
-  size_t off_qbf16, off_qnorm, off_qf32, off_qexact, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
+  size_t off_qbf16, off_qnorm, off_qlo, off_qf32, off_qexact, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
 };
 
 // row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
@@ -952,6 +953,7 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   size_t off = 0;
   L.off_qbf16 = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * row_elems * 2);
   L.off_qnorm = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);
+  L.off_qlo = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * 4);
   L.off_qf32 = off;  off += align256(static_cast<size_t>(B) * row_elems * 4);
   L.off_qexact = off; off += align256(static_cast<size_t>(B) * row_elems * 4);   // un-rounded queries (exact re-ranking)
   L.off_partial = off; off += align256(static_cast<size_t>(L.cpm) * B * k * 8);
@@ -1022,32 +1024,53 @@ static bool split_enabled() {
   return on;
 }
 
-int candidates_kept(int dtype, int k, int rerank) {
+int default_shadow_kind(int row_elems) {
+  const bool hi_ok = row_elems >= 8 && row_elems % 8 == 0 && ((row_elems + 15) / 16) * 8 <= kMaxKCols;
+  const bool hilo_ok = row_elems >= 16 && row_elems % 16 == 0 && row_elems <= kMaxKCols;
+  if (const char* e = getenv("RAG_B200_F32_SHADOW")) {
+    if (!strcmp(e, "hilo") && hilo_ok) return kShadowHiLo;
+    if (!strcmp(e, "hi") && hi_ok) return kShadowHi;
+  }
+  // measured (1M x 384 fp32, B = 32 / 1024): hi/lo 0.44 / 1.90 ms; hi-only with 64-entry heaps 1.16 / 2.12 ms -- the
+  // per-thread heap insertions of the list warm-up cost more than the two MMAs saved -- so hi-only is what rows the
+  // split cannot take get (dim > 384 or dim % 16 != 0), until its selection is cheaper
+  return hilo_ok ? kShadowHiLo : (hi_ok ? kShadowHi : kShadowNone);
+}
+
+int candidates_kept(int dtype, int k, int rerank, int shadow_kind) {
   if (dtype == 1 && !rerank) return k;
+  // hi-only filter of an fp32 store: bf16 rounding moves a unit-norm dot product by ~1e-3 worst case, so the list
+  // must reach that far beyond the k-th neighbour for the guard to certify it (1M x 384 unit-norm: ~rank 20-40)
+  if (dtype != 1 && shadow_kind == kShadowHi) return k <= 32 ? 64 : (k <= 100 ? 128 : k + 64);
   return k <= 10 ? 16 : k + 16;      // slack for the exact re-ranking of approximately ranked rows
 }
 
-bool supported(int dtype, int row_elems, int k, int space, int rerank) {
+bool supported(int dtype, int row_elems, int k, int space, int rerank, int shadow_kind) {
   (void)space;
   if (get_encode() == nullptr || k < 1) return false;
-  if (dtype == 1) return row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && candidates_kept(dtype, k, rerank) <= 1024;
+  if (dtype == 1) return row_elems >= 8 && ((row_elems + 15) / 16) * 8 <= kMaxKCols && candidates_kept(dtype, k, rerank, 0) <= 1024;
+  if (!split_enabled() || candidates_kept(dtype, k, 0, shadow_kind) > 1024) return false;
+  // fp32 rows as bf16(x): an ordinary bf16 contraction over the shadow (TMA needs 16-byte row pitches)
+  if (shadow_kind == kShadowHi) return row_elems >= 8 && row_elems % 8 == 0 && ((row_elems + 15) / 16) * 8 <= kMaxKCols;
   // fp32 rows as [hi | lo] bf16: the A operand takes row_elems TMEM columns; k-steps must not straddle hi/lo
-  return split_enabled() && row_elems >= 16 && row_elems % 16 == 0 && row_elems <= kMaxKCols &&
-         candidates_kept(dtype, k, 0) <= 1024;
+  if (shadow_kind == kShadowHiLo) return row_elems >= 16 && row_elems % 16 == 0 && row_elems <= kMaxKCols;
+  return false;
 }
 
-size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count, int rerank) {
-  if (!supported(dtype, row_elems, k, 0, rerank)) return 0;
-  const int width = dtype == 1 ? row_elems : 2 * row_elems;
-  return make_layout(width, B, candidates_kept(dtype, k, rerank), sm_count).total;
+size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count, int rerank, int shadow_kind) {
+  if (!supported(dtype, row_elems, k, 0, rerank, shadow_kind)) return 0;
+  const int width = (dtype != 1 && shadow_kind == kShadowHiLo) ? 2 * row_elems : row_elems;
+  return make_layout(width, B, candidates_kept(dtype, k, rerank, shadow_kind), sm_count).total;
 }
 
 cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches) {
-  if (!supported(p.dtype, p.row_elems, p.k, p.space, p.rerank)) return cudaErrorNotSupported;
-  const bool split = (p.dtype != 1);
+  if (!supported(p.dtype, p.row_elems, p.k, p.space, p.rerank, p.shadow_kind)) return cudaErrorNotSupported;
+  const bool f32 = (p.dtype != 1);
+  const bool split = f32 && p.shadow_kind == kShadowHiLo;        // [hi | lo] rows, three MMAs per k-step
+  const bool hi_only = f32 && p.shadow_kind == kShadowHi;        // bf16(x) rows: an ordinary bf16 contraction
   const int width = split ? 2 * p.row_elems : p.row_elems;       // bf16 elements per streamed row
-  const int kk = candidates_kept(p.dtype, p.k, p.rerank);
-  if (split && p.shadow == nullptr) return cudaErrorInvalidValue;
+  const int kk = candidates_kept(p.dtype, p.k, p.rerank, p.shadow_kind);
+  if (f32 && p.shadow == nullptr) return cudaErrorInvalidValue;
   const Layout L = make_layout(width, p.B, kk, p.sm_count);
   __nv_bfloat16* q_bf16 = reinterpret_cast<__nv_bfloat16*>(p.scratch + L.off_qbf16);
   float* q_norm = reinterpret_cast<float*>(p.scratch + L.off_qnorm);
@@ -1059,8 +1082,11 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   if (e != cudaSuccess) return e;
   PrepArgs pa{};
   pa.src = p.queries_raw; pa.B = p.B; pa.dim = p.dim; pa.row_elems = p.row_elems;
-  pa.normalise = (p.space == 1); pa.round_bf16 = split ? 0 : 1; pa.split = split ? 1 : 0;
+  // fp32 stores: q_f32 and |q|^2 stay un-rounded (the refinement and the norms are exact; only the A operand is bf16)
+  pa.normalise = (p.space == 1); pa.round_bf16 = f32 ? 0 : 1; pa.split = split ? 1 : 0;
   pa.q_f32 = q_f32; pa.q_bf16 = q_bf16; pa.q_norm2 = q_norm;
+  float* q_lo = reinterpret_cast<float*>(p.scratch + L.off_qlo);
+  pa.q_lo_norm2 = hi_only ? q_lo : nullptr;
   float* q_exact = reinterpret_cast<float*>(p.scratch + L.off_qexact);
   pa.q_exact = p.rerank ? q_exact : nullptr; pa.exact_elems = p.exact_elems;
   e = launch_prep_queries(pa, st);
@@ -1081,7 +1107,7 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
               : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   }
   CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                            const_cast<void*>(split ? static_cast<const void*>(p.shadow) : p.vectors), gdim, gstride, box,
+                            const_cast<void*>(f32 ? static_cast<const void*>(p.shadow) : p.vectors), gdim, gstride, box,
                             estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
@@ -1136,6 +1162,7 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   out->S = L.cpm;
   out->k_kept = kk;
   out->q_norm2 = q_norm;
+  out->q_lo_norm2 = hi_only ? q_lo : nullptr;
   out->q_f32 = q_f32;
   out->q_exact = q_exact;
   out->merged = reinterpret_cast<uint64_t*>(p.scratch + L.off_merged);

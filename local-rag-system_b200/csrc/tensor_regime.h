@@ -17,7 +17,8 @@ constexpr int kStreamMaxBatchF32 = 6;
 
 struct Problem {
   const void* vectors;      // [n_rows][row_elems] bf16 (or fp32 when `shadow` is streamed instead), row-major
-  const void* shadow;       // fp32 stores: [n_rows][hi(row_elems) | lo(row_elems)] bf16 split of the rows
+  const void* shadow;       // fp32 stores: bf16 shadow of the rows, [n_rows][hi | lo] (kShadowHiLo) or [n_rows][hi] (kShadowHi)
+  int shadow_kind;          // kernels.h: kShadowNone (bf16 stores), kShadowHi, kShadowHiLo
   const float* norms2;      // [n_rows] |x|^2 of the stored rows (l2 space)
   const float* min_norm2;   // [1] lower bound of norms2 over everything the store ever held
   int64_t n_rows;
@@ -34,17 +35,23 @@ struct Problem {
   int sm_count;
 };
 
-bool supported(int dtype, int row_elems, int k, int space, int rerank);
+// shadow_kind: which bf16 shadow an fp32 store is contracted through (ignored for bf16 stores)
+bool supported(int dtype, int row_elems, int k, int space, int rerank, int shadow_kind);
+// the shadow a NEW fp32 store of this row length starts with (RAG_B200_F32_SHADOW=hi|hilo overrides):
+// kShadowHi where the kernel can take it, else kShadowHiLo, else kShadowNone (no tensor regime for the store)
+int default_shadow_kind(int row_elems);
 // candidates the kernel keeps per query: k for bf16 stores (exact ranking of the stored values);
-// more for fp32 stores, whose rows are ranked through a bf16 hi/lo split and re-ranked exactly
+// more for fp32 stores, whose rows are ranked through a bf16 shadow and re-ranked exactly -- k + 6..16 behind the
+// hi/lo split (error ~1e-6), 64..128 behind the hi-only filter (error ~1e-3) --
 // (and for bf16 stores that keep an un-rounded fp32 plane: ranked in bf16, re-ranked against the plane)
-int candidates_kept(int dtype, int k, int rerank);
-size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count, int rerank);
+int candidates_kept(int dtype, int k, int rerank, int shadow_kind);
+size_t scratch_bytes(int dtype, int row_elems, int B, int k, int sm_count, int rerank, int shadow_kind);
 struct Result {
   const uint64_t* partial;  // [S][B][k_kept] ascending candidate lists per query (inside `scratch`)
   int S;
   int k_kept;               // list length: k, or k + slack when ranking was approximate (fp32 stores)
   const float* q_norm2;     // [B] |prepared query|^2
+  const float* q_lo_norm2;  // [B] |q - bf16(q)|^2 (kShadowHi only, else nullptr)
   const float* q_f32;       // [B][row_elems] prepared queries (for the l2 refinement)
   const float* q_exact;     // [B][exact_elems] normalised, un-rounded queries (Problem::rerank)
   uint64_t* merged;         // [B][k_kept] scratch for the merged keys before refinement

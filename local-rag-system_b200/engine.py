@@ -235,6 +235,21 @@ class DeviceStore:
         return {"kernel_ms": ms.value, "regime": {0: None, 1: "stream", 2: "tensor"}[regime.value],
                 "launches": launches.value}
 
+    def set_f32_shadow(self, kind: str = "auto"):
+        """fp32 stores: pin the bf16 shadow the tensor regime contracts ("hi": bf16(x) filter, "hilo": split
+        precision) or hand the choice back to the store ("auto"); include/rag_b200.h, rag_store_set_f32_shadow."""
+        kinds = {"auto": N.F32_SHADOW_AUTO, "hi": N.F32_SHADOW_HI, "hilo": N.F32_SHADOW_HILO}
+        if kind not in kinds:
+            raise ValueError(f"shadow kind must be one of {sorted(kinds)}, got {kind!r}")
+        N.check(self._lib.rag_store_set_f32_shadow(self._h, kinds[kind]))
+
+    def f32_tensor_info(self):
+        """Shadow kind in force and how many tensor-regime queries of this fp32 store were served / had to be
+        re-run on the exact stream kernel because the guard could not certify them."""
+        kind, q, r = C.c_int32(), C.c_int64(), C.c_int64()
+        N.check(self._lib.rag_store_f32_tensor_info(self._h, C.byref(kind), C.byref(q), C.byref(r)))
+        return {"shadow": {0: None, 1: "hi", 2: "hilo"}[kind.value], "queries": q.value, "reruns": r.value}
+
 
 class ShardedDeviceStore:
     """One corpus over several devices of THIS process (include/rag_b200.h, rag_sharded_*): same

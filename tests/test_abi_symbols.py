@@ -40,7 +40,7 @@ def test_only_the_abi_is_exported():
 
 def test_host_side_key_helpers():
     lib = _native.load()
-    assert lib.rag_abi_version() == _native.ABI_VERSION == 2
+    assert lib.rag_abi_version() == _native.ABI_VERSION == 3
     vals = [-2.5, -0.0, 0.0, 2.0 ** -100, 0.25, 1.0, 3.5, float("inf")]
     keys = [lib.rag_key_pack(v, 7) for v in vals]
     assert keys == sorted(keys)                      # ordered like the floats

@@ -382,9 +382,9 @@ def test_auto_regime_switches_on_batch_size():
         assert st.last_query_info()["regime"] == "tensor"
         f32.query(x[:6], 5)                                # fp32: up to 6 queries stay on the exact stream kernel
         assert f32.last_query_info()["regime"] == "stream"
-        f32.query(x[:64], 5)                               # beyond that: split-precision contraction + exact re-rank
+        f32.query(x[:64], 5)                               # beyond that: bf16-shadow contraction + exact re-rank
         assert f32.last_query_info()["regime"] == "tensor"
-        odd = DeviceStore(100, "f32", "cosine")            # hi/lo k-steps need dim % 16 == 0: stays on the stream kernel
+        odd = DeviceStore(100, "f32", "cosine")            # no shadow fits (row pitch % 8 != 0): stays on the stream kernel
         try:
             odd.upsert(unit_rows(500, 100, 2))
             odd.query(unit_rows(64, 100, 3), 5)
@@ -399,9 +399,10 @@ def test_auto_regime_switches_on_batch_size():
 
 
 # ------------------------------------------------------------------------------------
-# tensor regime on fp32 stores: rows contracted as bf16 hi/lo pairs (3 MMAs per k-step),
-# k + slack candidates re-ranked exactly from the fp32 rows, uncertifiable queries re-run
-# on the exact stream kernel.  Held to the fp32 bar, not the bf16 one.
+# tensor regime on fp32 stores: rows contracted through a bf16 shadow -- bf16(x) alone ("hi": a filter
+# that keeps 64-128 candidates) or hi/lo pairs ("hilo": 3 MMAs per k-step, k + slack candidates) --
+# candidates re-ranked exactly from the fp32 rows, uncertifiable queries re-run on the exact stream
+# kernel.  Held to the fp32 bar, not the bf16 one.
 # ------------------------------------------------------------------------------------
 SPLIT_CASES = [
     # space, n, dim, B, k
@@ -413,10 +414,19 @@ SPLIT_CASES = [
     ("cosine", 37, 48, 12, 10),           # fewer rows than one tile
     ("cosine", 20000, 384, 1024, 10),     # config 2's batch shape on a small corpus
 ]
+# rows longer than the hi/lo split can take (its A operand is 2 x dim bf16 <= 768) or not a multiple of 16:
+# only the hi-only shadow serves them
+HI_ONLY_CASES = [
+    ("cosine", 6000, 768, 32, 10),        # bge-base shape in fp32
+    ("l2", 3000, 768, 200, 10),           # two query tiles: cta_group::2 pairs
+    ("ip", 4000, 512, 64, 20),
+    ("cosine", 2500, 392, 16, 10),        # dim % 16 == 8
+    ("l2", 700, 24, 9, 5),
+    ("cosine", 5000, 640, 1024, 100),
+]
 
 
-@pytest.mark.parametrize("space,n,dim,B,k", SPLIT_CASES)
-def test_fp32_tensor_regime_matches_oracle(space, n, dim, B, k):
+def _split_case(space, n, dim, B, k, shadow):
     rng = np.random.default_rng(n * 5 + dim + B + k)
     x = rng.standard_normal((n, dim)).astype(np.float32) if space != "cosine" else unit_rows(n, dim, n)
     q = rng.standard_normal((B, dim)).astype(np.float32)
@@ -424,18 +434,104 @@ def test_fp32_tensor_regime_matches_oracle(space, n, dim, B, k):
     st = DeviceStore(dim, "f32", space)
     try:
         st.upsert(x)
+        st.set_f32_shadow(shadow)
         stored = st.fetch(np.arange(n))
         rows, dists, counts = st.query(q, k, regime="tensor")
         assert st.last_query_info()["regime"] == "tensor"
+        info = st.f32_tensor_info()
+        assert info["shadow"] == shadow and info["queries"] == B and 0 <= info["reruns"] <= B
         check_against_oracle(space, "f32", stored, q, k, rows, dists, counts, min_recall=1.0)
         r2, d2, c2 = st.query(q, k, regime="stream")
         assert np.array_equal(c2, counts)
         assert np.allclose(dists, d2, rtol=1e-5, atol=2e-6)
+        return info
     finally:
         st.close()
 
 
-def test_fp32_tensor_regime_near_ties_are_decided_exactly():
+@pytest.mark.parametrize("shadow", ["hi", "hilo"])
+@pytest.mark.parametrize("space,n,dim,B,k", SPLIT_CASES)
+def test_fp32_tensor_regime_matches_oracle(space, n, dim, B, k, shadow):
+    _split_case(space, n, dim, B, k, shadow)
+
+
+@pytest.mark.parametrize("space,n,dim,B,k", HI_ONLY_CASES)
+def test_fp32_tensor_regime_hi_only_shapes(space, n, dim, B, k):
+    """fp32 rows the split-precision shadow cannot take (dim > 384 or dim % 16 != 0): contracted as bf16(x),
+    re-ranked exactly, certified by the guard or re-run -- held to the fp32 bar all the same."""
+    st = DeviceStore(dim, "f32", space)
+    try:
+        assert st.f32_tensor_info()["shadow"] == "hi"            # what a new store starts with
+        if dim > 384 or dim % 16:
+            with pytest.raises(ValueError):
+                st.set_f32_shadow("hilo")
+    finally:
+        st.close()
+    _split_case(space, n, dim, B, k, "hi")
+
+
+def test_fp32_hi_only_filter_certifies_spread_out_rows():
+    """On rows as spread out as unit-norm Gaussians the hi-only filter certifies (nearly) every query itself:
+    the exact re-run stays the exception, and the store keeps the cheaper shadow."""
+    n, dim, k, B = 50_000, 384, 10, 256
+    x = unit_rows(n, dim, 5)
+    q = unit_rows(B, dim, 6)
+    st = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        st.set_f32_shadow("hi")
+        for _ in range(3):
+            rows, dists, counts = st.query(q, k)
+        assert st.last_query_info()["regime"] == "tensor"
+        info = st.f32_tensor_info()
+        assert info["shadow"] == "hi" and info["queries"] == 3 * B
+        assert info["reruns"] <= info["queries"] // 50, info
+        check_against_oracle("cosine", "f32", x, q, k, rows, dists, counts, min_recall=1.0)
+    finally:
+        st.close()
+
+
+def test_fp32_store_moves_to_split_precision_when_the_filter_cannot_certify():
+    """Rows packed far closer than bf16 can tell apart: the hi-only guard sends most queries to the exact
+    re-run (answers stay exact), the store notices and moves to the hi/lo split, which certifies them."""
+    n, dim, k, B = 6000, 256, 10, 96
+    rng = np.random.default_rng(9)
+    centre = unit_rows(1, dim, 8)[0]
+    # cosine distances 0.1 +- 0.009: rank 10 and rank 64 of a query are ~5e-3 apart (the hi-only bound is 8e-3),
+    # rank 10 and rank 16 ~1e-3 (the split-precision bound is 2.4e-4) -- simulated in numpy when this was written
+    x = centre[None, :] + 2e-2 * rng.standard_normal((n, dim)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = centre[None, :] + 2e-2 * rng.standard_normal((B, dim)).astype(np.float32)
+    st = DeviceStore(dim, "f32", "cosine")
+    try:
+        st.upsert(x)
+        stored = st.fetch(np.arange(n))
+        if st.f32_tensor_info()["shadow"] != "hi":
+            pytest.skip("stores of this shape start on the hi/lo split: nothing to move away from")
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        first = st.f32_tensor_info()
+        assert first["reruns"] > B // 8, first                      # the filter alone could not decide these
+        check_against_oracle("cosine", "f32", stored, q, k, rows, dists, counts, min_recall=1.0)
+        rows, dists, counts = st.query(q, k, regime="tensor")       # the switch happens ahead of this search
+        second = st.f32_tensor_info()
+        assert second["shadow"] == "hilo", second
+        check_against_oracle("cosine", "f32", stored, q, k, rows, dists, counts, min_recall=1.0)
+        rows, dists, counts = st.query(q, k, regime="tensor")
+        third = st.f32_tensor_info()
+        assert third["reruns"] - second["reruns"] <= B // 8, (second, third)       # split precision certifies them
+        rs, ds, cs = st.query(q, k, regime="stream")
+        assert np.array_equal(rows, rs) and np.allclose(dists, ds, rtol=1e-5, atol=2e-6)
+        st.set_f32_shadow("hi")                                     # pinned: the policy keeps its hands off
+        for _ in range(3):
+            rows, dists, counts = st.query(q, k, regime="tensor")
+        assert st.f32_tensor_info()["shadow"] == "hi"
+        check_against_oracle("cosine", "f32", stored, q, k, rows, dists, counts, min_recall=1.0)
+    finally:
+        st.close()
+
+
+@pytest.mark.parametrize("shadow", ["hi", "hilo"])
+def test_fp32_tensor_regime_near_ties_are_decided_exactly(shadow):
     """More near-identical rows than the candidate slack: the approximate ranking cannot tell
     them apart, the guard must notice and the exact stream kernel must decide -- the result is
     then the stream regime's, bit for bit."""
@@ -443,7 +539,7 @@ def test_fp32_tensor_regime_near_ties_are_decided_exactly():
     x = unit_rows(n, dim, 31)
     rng = np.random.default_rng(32)
     base = x[100].copy()
-    cluster = np.arange(1000, 1060)
+    cluster = np.arange(1000, 1000 + (60 if shadow == "hilo" else 200))      # more than the candidates either shadow keeps
     x[cluster] = base[None, :] + 2e-7 * rng.standard_normal((cluster.size, dim)).astype(np.float32)
     q = unit_rows(B, dim, 33)
     q[3] = base
@@ -451,8 +547,10 @@ def test_fp32_tensor_regime_near_ties_are_decided_exactly():
     st = DeviceStore(dim, "f32", "cosine")
     try:
         st.upsert(x)
+        st.set_f32_shadow(shadow)
         stored = st.fetch(np.arange(n))
         rt, dt, ct = st.query(q, k, regime="tensor")
+        assert st.f32_tensor_info()["reruns"] >= 2
         rs, ds, cs = st.query(q, k, regime="stream")
         assert np.array_equal(rt[[3, 17]], rs[[3, 17]]) and np.array_equal(dt[[3, 17]], ds[[3, 17]])
         assert np.array_equal(rt, rs) and np.allclose(dt, ds, rtol=1e-5, atol=2e-6)
@@ -461,8 +559,9 @@ def test_fp32_tensor_regime_near_ties_are_decided_exactly():
         st.close()
 
 
-def test_fp32_tensor_regime_shadow_follows_writes():
-    """The hi/lo shadow is built on first use, kept in step by in-place upserts and appends,
+@pytest.mark.parametrize("shadow", ["hi", "hilo"])
+def test_fp32_tensor_regime_shadow_follows_writes(shadow):
+    """The bf16 shadow is built on first use, kept in step by in-place upserts and appends,
     dropped when the store grows and rebuilt; tombstones and `where` masks apply as usual."""
     n, dim, k, B = 3000, 128, 10, 40
     x = unit_rows(n, dim, 41)
@@ -471,6 +570,7 @@ def test_fp32_tensor_regime_shadow_follows_writes():
     st = DeviceStore(dim, "f32", "l2", capacity_hint=4096)
     try:
         st.upsert(x)
+        st.set_f32_shadow(shadow)
         rows, dists, counts = st.query(q, k, regime="tensor")           # builds the shadow
         check_against_oracle("l2", "f32", x, q, k, rows, dists, counts)
         winners = rows[:, 0].copy()
