@@ -581,6 +581,7 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
   if (regime == 2) {
     if (timed) CUDA_TRY(cudaEventRecord(c->ev0, st));
     tensor::Problem p{};
+    p.max_norm2 = s->d_max_norm2; p.lo_max2 = s->d_max_norm2 + 2;
     p.vectors = s->d_vectors; p.shadow = s->d_shadow; p.shadow_kind = (s->dtype == RAG_DTYPE_F32) ? s->shadow_kind : kShadowNone; p.norms2 = s->d_norms2; p.min_norm2 = s->d_max_norm2 + 1; p.n_rows = s->rows; p.row_elems = s->row_elems;
     p.dim = s->dim; p.dtype = s->dtype; p.space = s->space;
     p.live = s->d_live; p.filter = filter; p.filter_words = fwords;
@@ -671,11 +672,17 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
     ra.out_keys = out.keys; ra.out_rows = out.rows; ra.out_dists = out.dists; ra.out_counts = out.counts;
     if (split) {
       CUDA_TRY(cudaMemsetAsync(d_redo, 0, sizeof(int), st));
-      ra.guard_rel = 1.2e-4f; ra.q_norm2 = tres.q_norm2; ra.x_max_norm2 = s->d_max_norm2;
+      ra.guard_rel = kGuardRel; ra.q_norm2 = tres.q_norm2; ra.x_max_norm2 = s->d_max_norm2;
       ra.q_lo_norm2 = tres.q_lo_norm2; ra.x_lo_max2 = s->d_max_norm2 + 2;      // hi-only shadow: the bf16 rounding it ignores
       ra.redo_count = d_redo; ra.redo_list = d_redo + 1;
     }
-    CUDA_TRY(launch_refine(ra, st));
+    if (split && tres.filt) {      // hi-only filter: every row within 2 eps of the approximate k-th best is re-scored
+      RefineFilterArgs fa{};
+      fa.r = ra; fa.extra = tres.extra; fa.extra_cnt = tres.extra_cnt; fa.S = tres.S; fa.cap = tres.extra_cap;
+      CUDA_TRY(launch_refine_filter(fa, st));
+    } else {
+      CUDA_TRY(launch_refine(ra, st));
+    }
     launches++;
     if (split) {
       // statistics: how many queries the guard sends to the re-run (read when this context searches again)

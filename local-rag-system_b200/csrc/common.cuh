@@ -70,6 +70,19 @@ __host__ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 #ifdef __CUDACC__
+// ---- error bound of a bf16 contraction of fp32 vectors ----------------------------------------------
+// |q.x - bf16(q).bf16(x)| <= |q - qh| |x| + |qh| |x - xh| (Cauchy-Schwarz) with |q - qh| known per query and |x|,
+// |x - xh| bounded by their maxima over the store, plus guard_rel |q||x| for the fp32 accumulation and the
+// rounding of the distances themselves.  l2 distances |q|^2 + |x|^2 - 2 q.x move by twice that.  Used by the
+// hi-only filter of fp32 stores (tensor_regime.cu) and by the kernels that certify its result (merge.cu): both
+// sides must compute the SAME number, hence one function.  Arguments are squared norms.
+__device__ __forceinline__ float bf16_contraction_eps(float q_norm2, float q_lo_norm2, float x_max_norm2, float x_lo_max2,
+                                                      float guard_rel, bool l2) {
+  const float qn = sqrtf(q_norm2), xn = sqrtf(x_max_norm2), ql = sqrtf(q_lo_norm2), xl = sqrtf(x_lo_max2);
+  const float eps = guard_rel * qn * xn + 1.01f * (ql * xn + (qn + ql) * xl);
+  return l2 ? 2.0f * eps : eps;
+}
+
 // ---- streaming 16-byte load: read-only path, do not allocate in L1 ---------
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   uint4 r;

@@ -135,6 +135,22 @@ struct RefineArgs {
   int32_t* out_counts;
 };
 cudaError_t launch_refine(const RefineArgs& a, cudaStream_t st);
+constexpr float kGuardRel = 1.2e-4f;      // fp32 accumulation + distance rounding, relative to |q| max|x|
+
+// Hi-only FILTER mode (fp32 store contracted as bf16(q).bf16(x), k <= 16; tensor_regime.h, Result::filt).
+// `keys` = the merged approximate top-k (k_in entries per query); A_k = its k-th distance.  With
+// eps = bf16_contraction_eps() >= |approx - exact|: the approximate top-k rows all have exact <= A_k + eps, so the
+// exact k-th best is <= A_k + eps, so every row of the exact top-k has approx <= A_k + 2 eps.  The contraction left,
+// per (CTA, query), every row within 2 eps of a bound >= A_k (`extra`): all rows within 2 eps of A_k are re-scored
+// from the fp32 rows, sorted, and the best k emitted -- exact, no a-posteriori guard.  A query whose buffers
+// overflowed (more candidates within 2 eps than they hold) goes to redo_list instead.  Uses RefineArgs' fields plus:
+struct RefineFilterArgs {
+  RefineArgs r;             // keys / vectors / queries / k / k_in / l2 / guard_rel / norms / redo_* / outputs as above
+  const uint64_t* extra;    // [S][B][cap]
+  const int* extra_cnt;     // [S][B]
+  int S, cap;
+};
+cudaError_t launch_refine_filter(const RefineFilterArgs& a, cudaStream_t st);
 
 // ---- K1: normalise / convert on upsert ------------------------------------------
 struct UpsertArgs {

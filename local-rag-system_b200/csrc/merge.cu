@@ -222,13 +222,9 @@ __global__ void __launch_bounds__(kMergeThreads) refine_kernel(const RefineArgs 
     if (worst_in != kEmptyKey && keys[k - 1] != kEmptyKey) {
       const float a_max = key_dist(worst_in);
       const float d_k = key_dist(keys[k - 1]);
-      const float qn = sqrtf(a.q_norm2[b]), xn = sqrtf(a.x_max_norm2[0]);
-      float eps = a.guard_rel * qn * xn;
-      if (a.q_lo_norm2 != nullptr) {      // hi-only contraction: what rounding q and x to bf16 can have moved (kernels.h)
-        const float ql = sqrtf(a.q_lo_norm2[b]), xl = sqrtf(a.x_lo_max2[0]);
-        eps += 1.01f * (ql * xn + (qn + ql) * xl);
-      }
-      if (a.l2) eps *= 2.0f;
+      // hi-only contraction: plus what rounding q and x to bf16 can have moved (common.cuh)
+      const float eps = bf16_contraction_eps(a.q_norm2[b], a.q_lo_norm2 ? a.q_lo_norm2[b] : 0.0f, a.x_max_norm2[0],
+                                             a.q_lo_norm2 ? a.x_lo_max2[0] : 0.0f, a.guard_rel, a.l2 != 0);
       if (!(a_max - d_k > 2.0f * eps)) a.redo_list[atomicAdd(a.redo_count, 1)] = b;
     }
   }
@@ -255,7 +251,85 @@ __global__ void __launch_bounds__(kMergeThreads) refine_kernel(const RefineArgs 
   }
 }
 
+// ---- hi-only filter: exact re-scoring of every row within 2 eps of the approximate k-th best (kernels.h) ------
+constexpr int kFiltRefineCap = 512;       // candidates per query the re-scoring takes; more -> exact re-run
+__global__ void __launch_bounds__(kMergeThreads) refine_filter_kernel(const RefineFilterArgs fa) {
+  const RefineArgs& a = fa.r;
+  __shared__ uint64_t cand[kFiltRefineCap];
+  __shared__ int s_n, s_over;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int k = a.k;
+  if (threadIdx.x == 0) { s_n = 0; s_over = 0; }
+  for (int i = threadIdx.x; i < kFiltRefineCap; i += blockDim.x) cand[i] = kEmptyKey;
+  __syncthreads();
+  // threshold: approximate k-th best + 2 eps (+inf while fewer than k rows exist: everything buffered is a candidate)
+  float thr = __int_as_float(0x7f800000);
+  const uint64_t kth = a.keys[static_cast<size_t>(b) * a.k_in + (k - 1)];
+  if (kth != kEmptyKey)
+    thr = key_dist(kth) + 2.0f * bf16_contraction_eps(a.q_norm2[b], a.q_lo_norm2[b], a.x_max_norm2[0], a.x_lo_max2[0],
+                                                       a.guard_rel, a.l2 != 0);
+  for (int idx = threadIdx.x; idx < fa.S * fa.cap; idx += blockDim.x) {
+    const int c = idx / fa.cap, i = idx - c * fa.cap;
+    const size_t slot = static_cast<size_t>(c) * a.B + b;
+    const int cnt = fa.extra_cnt[slot];
+    if (cnt < 0) { if (i == 0) atomicExch(&s_over, 1); continue; }
+    if (i >= cnt) continue;
+    const uint64_t key = fa.extra[slot * fa.cap + i];
+    if (key_dist(key) <= thr) {
+      const int p = atomicAdd(&s_n, 1);
+      if (p < kFiltRefineCap) cand[p] = key; else atomicExch(&s_over, 1);
+    }
+  }
+  __syncthreads();
+  const int n = min(s_n, kFiltRefineCap);
+  const float* q = a.queries + static_cast<size_t>(b) * a.row_elems;
+  for (int j = warp; j < n; j += kMergeWarps) {       // one warp per candidate, the stream kernel's direct fp32 arithmetic
+    const uint32_t row = key_row(cand[j]);
+    const float* x = reinterpret_cast<const float*>(a.vectors) + static_cast<size_t>(row) * a.row_elems;
+    float acc = 0.0f;
+    for (int e = lane; e < a.row_elems; e += 32) {
+      if (a.l2) { const float d = x[e] - q[e]; acc = fmaf(d, d, acc); } else { acc = fmaf(x[e], q[e], acc); }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    __syncwarp();
+    if (lane == 0) cand[j] = make_key(a.l2 ? acc : 1.0f - acc, row);
+  }
+  __syncthreads();
+  int npad = next_pow2(n > k ? n : k);
+  if (npad > kFiltRefineCap) npad = kFiltRefineCap;
+  block_bitonic_sort(cand, npad);
+  if (threadIdx.x == 0 && s_over && a.redo_count != nullptr) a.redo_list[atomicAdd(a.redo_count, 1)] = b;
+  int cnt = 0;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    uint64_t key = cand[j];
+    const bool valid = key != kEmptyKey;
+    if (valid) { key = key_to_global(a.rows_map, key); cnt++; }
+    const size_t o = static_cast<size_t>(b) * k + j;
+    if (a.out_keys) a.out_keys[o] = key;
+    if (a.out_rows) a.out_rows[o] = valid ? static_cast<int64_t>(key_row(key)) : -1;
+    if (a.out_dists) a.out_dists[o] = valid ? key_dist(key) : __int_as_float(0x7f800000);
+  }
+  if (a.out_counts) {
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&total, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) a.out_counts[b] = total;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_refine_filter(const RefineFilterArgs& a, cudaStream_t st) {
+  if (a.r.B <= 0 || a.r.k <= 0 || a.r.k_in < a.r.k || a.r.k > kFiltRefineCap || a.S <= 0 || a.cap <= 0) return cudaErrorInvalidValue;
+  if (a.r.dtype == 1 || a.r.q_lo_norm2 == nullptr || a.r.x_lo_max2 == nullptr) return cudaErrorInvalidValue;
+  refine_filter_kernel<<<a.r.B, kMergeThreads, 0, st>>>(a);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_refine(const RefineArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.k <= 0 || a.k_in < a.k) return cudaErrorInvalidValue;

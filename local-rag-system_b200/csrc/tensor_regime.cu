@@ -277,6 +277,7 @@ struct Args {
   int prefetch;                  // L2 prefetch distance in tiles (0 = off)
   int nbuf;                      // accumulator buffers in tensor memory (2 or 4)
   int stages_used;               // ring stages in use (<= Ring<MODE>::kStages)
+  int one_issuer;                // 1: warp 1 issues every tile (the ring holds fewer than two whole tiles, see the MMA warps)
   int split_steps;               // > 0: split-precision rows [hi | lo], the first split_steps k-steps are hi
   uint64_t* partial;             // [cpm][B][k]
   // [n_mtiles*128] ordered(fp32): smallest k-th-best distance any CTA has reached for this query so far.
@@ -296,7 +297,21 @@ struct Args {
   // (without pacing the siblings drift apart and every tile is read from DRAM about twice).
   uint32_t* progress;
   uint32_t pace_window;          // tiles a cluster may run ahead of its slowest sibling
+  // FILT (hi-only shadow of an fp32 store, k <= 16): the contraction ranks by bf16(q).bf16(x), which is within
+  // eps = bf16_contraction_eps() of the exact distance.  Every row of the exact top-k then lies within 2 eps of the
+  // approximate k-th best (see refine_filter_kernel), so next to its top-k list every epilogue thread keeps ALL rows
+  // within `2 eps` of its running bound in a small buffer; the survivors are re-scored exactly afterwards.
+  const float* q_lo_norm2;       // [B] |q - bf16(q)|^2
+  const float* x_max_norm2;      // [1] max |x|^2 over the store
+  const float* x_lo_max2;        // [1] max |x - bf16(x)|^2 over the store
+  float guard_rel;
+  uint64_t* extra;               // [cpm][B][kFiltCap] buffered keys (unordered)
+  int* extra_cnt;                // [cpm][B] entries, -1 = the buffer overflowed (the query is re-run exactly)
 };
+// buffer entries per (CTA, query); 128 threads x 64 x 8 B = 64 KB of shared memory.  A thread ends with k rows + those
+// in the 2 eps band above its bound (1M x 768 unit-norm rows over 148 CTAs: ~20 +- 4); 32 entries overflowed for
+// 1.5 % of the queries (any of the 148 CTAs of a query), and an overflow costs an exact re-run
+constexpr int kFiltCap = 64;
 constexpr size_t kPaceBytes = 56u << 20;  // L2 budget (of 126 MB) for the tiles between the slowest and the fastest sibling
 
 // per-thread running top-k.
@@ -393,8 +408,9 @@ struct TopList {
 // for both (each tensor core contracts its own 128 queries with the 64 rows held by the pair), so a
 // corpus byte is written to and read from shared memory once per PAIR -- half the per-SM traffic of
 // the multicast scheme (which at 64 B/clk in + 64 B/clk out sat at the SM's shared-memory limit).
-template <int KL, bool L2, int MODE, int NB>
+template <int KL, bool L2, int MODE, int NB, bool FILT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_constant__ CUtensorMap tmap, const Args a) {
+  static_assert(!FILT || KL <= 16, "the filter buffers sit where the shared-memory heaps of larger k would");
   constexpr int CL = (MODE == 0) ? 1 : 2;
   constexpr bool PAIR = (MODE == 2);
   constexpr int kStages = Ring<MODE, NB>::kStages;
@@ -551,6 +567,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     uint32_t* q_row = use_q ? a.tau_q + static_cast<size_t>(mt * kM + m) * a.cpm : nullptr;
     const float qn = (L2 && q_valid) ? a.q_norm2[b] : 0.0f;
     const float base_n = L2 ? qn + __ldg(a.x_min_norm2) : 0.0f;
+    // FILT: rows within `margin` = 2 eps of the running bound are buffered (entry i of thread t at word i * 128 + t)
+    float margin = 0.0f;
+    uint64_t* fbuf = nullptr;
+    int fcnt = 0;
+    bool fover = false;
+    if constexpr (FILT) {
+      fbuf = reinterpret_cast<uint64_t*>(smem_raw + (bar_base + 512u - raw)) + (lg * 32 + lane);
+      if (q_valid)
+        margin = 2.0f * bf16_contraction_eps(a.q_norm2[b], a.q_lo_norm2[b], __ldg(a.x_max_norm2), __ldg(a.x_lo_max2),
+                                             a.guard_rel, L2);
+    }
 
     uint32_t it = 0;
     TileWalker walk(a, cj, n_tiles);
@@ -597,6 +624,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         const bool last_sub = (sub == NSUB - 1);
         uint32_t vv[2][32];
         const uint32_t acc_addr = tmem_acc + (static_cast<uint32_t>(lg * 32) << 16) + static_cast<uint32_t>(buf * kAccCols + sub * 64);
+        // tcgen05.ld / tcgen05.wait are .sync.aligned: the lanes, which leave the candidate loops of the previous
+        // tile one by one, must be back together here
+        __syncwarp();
         if ((w0 | w1) != 0u) {                           // a half with no passing row is not even read
           tmem_ld_x32(acc_addr, vv[0]);
           tmem_ld_x32(acc_addr + 32, vv[1]);
@@ -631,14 +661,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
         const float t4 = fmax3(n32[1], n32[2], n32[3]), t5 = fmax3(n32[4], n32[5], n32[6]);
         const float t6 = fmax3(n32[7], n32[8], n32[9]);
         const float best = fmax3(fmax3(t0, t1, t2), fmax3(t3, t4, t5), fmaxf(t6, n32[10]));
+        const float tau_r = FILT ? tau + margin : tau; // FILT: everything within `margin` of the bound is wanted
         float lb;                                      // lower bound on the dot product of any candidate of this lane
         if constexpr (L2) {
           // d = |q|^2 + |x|^2 - 2 q.x <= tau  =>  q.x >= (|q|^2 + min|x|^2 - tau) / 2 (minus rounding slack),
           // with min|x|^2 over everything the store ever held (tracked by the upsert kernel): no per-tile loads
-          lb = 0.5f * (base_n - tau) - 4e-7f * (fabsf(base_n) + fabsf(tau));
+          lb = 0.5f * (base_n - tau_r) - 4e-7f * (fabsf(base_n) + fabsf(tau_r));
         } else {
           // cosine / ip: fl(1 - dot) <= tau implies dot >= 1 - tau - 2^-24
-          lb = (1.0f - tau) - 1.2e-7f;
+          lb = (1.0f - tau_r) - 1.2e-7f;
         }
         if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
         if (a.stats && lane == 0) atomicAdd(&g_tensor_stats[1], 1ull);
@@ -652,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
   #pragma unroll
           for (int off = 16; off > 0; off >>= 1) xmin = fminf(xmin, __shfl_xor_sync(0xffffffffu, xmin, off));
           const float bn = qn + xmin;
-          lb = 0.5f * (bn - tau) - 4e-7f * (fabsf(bn) + fabsf(tau));
+          lb = 0.5f * (bn - tau_r) - 4e-7f * (fabsf(bn) + fabsf(tau_r));
           if (!__any_sync(0xffffffffu, q_valid && best >= lb)) continue;
           if (a.stats && lane == 0) atomicAdd(&g_tensor_stats[2], 1ull);
         }
@@ -706,6 +737,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
                   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q_row + cj), "r"(float_to_ordered(small_q)) : "memory");
               }
             }
+            if constexpr (FILT) {
+              if (dj <= tau + margin) {                // (tau = +inf until the list is full: everything is kept)
+                if (fcnt == kFiltCap) {                // full: drop what the bound has moved past since it was buffered
+                  const float thr = tau + margin;
+                  int w = 0;
+                  for (int i = 0; i < kFiltCap; ++i) {
+                    const uint64_t e = fbuf[i * kEpiThreads];
+                    if (key_dist(e) <= thr) { fbuf[w * kEpiThreads] = e; ++w; }
+                  }
+                  fcnt = w;
+                }
+                if (fcnt < kFiltCap) { fbuf[fcnt * kEpiThreads] = key; ++fcnt; }
+                else fover = true;                     // more than kFiltCap rows within the margin: exact re-run
+              }
+            }
             if (key < kth_key && dj <= tau_g) {
               if (a.stats) atomicAdd(&g_tensor_stats[4], 1ull);
               top.insert(key, k);
@@ -718,6 +764,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
             }
           }
         }
+      }
+    }
+    if constexpr (FILT) {
+      if (q_valid) {           // the buffered rows still within the margin of the final bound
+        const size_t slot = static_cast<size_t>(cj) * a.B + b;
+        const float thr = tau + margin;
+        uint64_t* out = a.extra + slot * kFiltCap;
+        int w = 0;
+        for (int i = 0; i < fcnt; ++i) {
+          const uint64_t e = fbuf[i * kEpiThreads];
+          if (key_dist(e) <= thr) out[w++] = e;
+        }
+        a.extra_cnt[slot] = fover ? -1 : w;
       }
     }
     // ---- emit this thread's list: partial[cj][b][0..k) ----
@@ -828,7 +887,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     while (walk.next(t, wt)) {
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
-      const bool mine = (it & 1u) == issuer;
+      // An issuer never looks at the full barriers of the other's tiles; with a ring of fewer than two whole tiles it
+      // can then get TWO phases ahead of a barrier (a stage whose next use belongs to the other issuer and has not
+      // even been loaded), where the parity test passes on stale data and the barriers receive arrivals out of phase
+      // (seen as launch failures with 4-5 stages at D = 768; a model of the protocol fails the same way for every
+      // ring shorter than 2 tiles and never for longer ones).  Short rings are therefore driven by ONE issuer.
+      const bool mine = a.one_issuer ? (issuer == 0u) : ((it & 1u) == issuer);
       ++it;
       if (!mine) {                                  // the other issuer's tile: step over its ring stages
         s += static_cast<uint32_t>(n_stages_per_tile);
@@ -927,7 +991,7 @@ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct Layout {
   int n_mtiles, cpm, cl, mode, nb;
-  size_t off_qbf16, off_qnorm, off_qlo, off_qf32, off_qexact, off_partial, off_tau, off_prog, off_tauq, off_merged, total;
+  size_t off_qbf16, off_qnorm, off_qlo, off_qf32, off_qexact, off_partial, off_tau, off_prog, off_tauq, off_merged, off_extra, off_extracnt, total;
 };
 
 // row_elems: width of the bf16 rows the kernel streams (2 x the store's for split precision); k: list length kept
@@ -961,22 +1025,24 @@ Layout make_layout(int row_elems, int B, int k, int sm_count) {
   L.off_prog = off; off += align256(static_cast<size_t>(L.cpm) * L.n_mtiles * 4);  // ... which also covers the pacing counters
   L.off_tauq = off; off += align256(static_cast<size_t>(L.n_mtiles) * kM * L.cpm * 4);   // ... and the quantile bounds
   L.off_merged = off; off += align256(static_cast<size_t>(B) * k * 8);
+  L.off_extra = off; off += align256(static_cast<size_t>(L.cpm) * B * kFiltCap * 8);      // FILT buffers (always sized: cheap)
+  L.off_extracnt = off; off += align256(static_cast<size_t>(L.cpm) * B * 4);
   L.total = off;
   return L;
 }
 
-template <int KL, bool L2, int MODE, int NB>
+template <int KL, bool L2, int MODE, int NB, bool FILT = false>
 cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t st) {
   constexpr int CL = (MODE == 0) ? 1 : 2;
   using R = Ring<MODE, NB>;
-  auto kern = gemm_topk_kernel<KL, L2, MODE, NB>;
+  auto kern = gemm_topk_kernel<KL, L2, MODE, NB, FILT>;
   // k <= 16: lists in registers, the whole 224 KB ring.  16 < k <= 128: the heaps take k x 128 x 8 bytes of shared
   // memory behind the barriers, the ring gets what is left (>= 96 KB; its depth does not limit the kernel: 4 stages
   // measured as fast as 14).  Larger k: heaps in local memory -> a short ring and the rest of the SM left to L1.
   const int per_tile = (a.row_elems + kStageK - 1) / kStageK;
-  int list_bytes = TopList<KL>::kShared ? a.k * kEpiThreads * 8 : 0;
-  if (list_bytes > 0 && (kRingBytes - list_bytes) / R::kStageBytes < per_tile + 1) list_bytes = 0;   // no room: heaps in local memory
-  a.lists_in_smem = list_bytes > 0 ? 1 : 0;
+  int list_bytes = TopList<KL>::kShared ? a.k * kEpiThreads * 8 : (FILT ? kFiltCap * kEpiThreads * 8 : 0);
+  if (!FILT && list_bytes > 0 && (kRingBytes - list_bytes) / R::kStageBytes < per_tile + 1) list_bytes = 0;   // no room: heaps in local memory
+  a.lists_in_smem = (!FILT && list_bytes > 0) ? 1 : 0;
   a.stages_used = R::kStages;
   if (list_bytes > 0) a.stages_used = std::min(R::kStages, (kRingBytes - list_bytes) / R::kStageBytes);
   else if (KL > 16) a.stages_used = std::min(4, (96 * 1024) / R::kStageBytes);
@@ -986,6 +1052,8 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
   }
   // the ring must hold at least one whole tile plus a stage, or producer and issuer wait for each other
   if (a.stages_used < per_tile + 1) a.stages_used = std::min(per_tile + 1, R::kStages);
+  a.one_issuer = (a.stages_used < 2 * per_tile) ? 1 : 0;
+  if (const char* ev = getenv("RAG_B200_TENSOR_ONE_ISSUER")) { if (atoi(ev) == 1) a.one_issuer = 1; }
   const int smem_bytes = a.stages_used * R::kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + list_bytes;
   if (smem_bytes > kSmemBytes) return cudaErrorInvalidConfiguration;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -1006,6 +1074,13 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, tmap, a);
+}
+
+// the hi-only filter of fp32 stores (k <= 16): single CTAs or cta_group::2 pairs, 64-row tiles
+cudaError_t launch_filter(const CUtensorMap& tmap, const Args& a, bool l2, int mode, dim3 grid, cudaStream_t st) {
+  if (mode == 2) return l2 ? launch_one<16, true, 2, kNB, true>(tmap, a, grid, st) : launch_one<16, false, 2, kNB, true>(tmap, a, grid, st);
+  if (mode == 0) return l2 ? launch_one<16, true, 0, kNB, true>(tmap, a, grid, st) : launch_one<16, false, 0, kNB, true>(tmap, a, grid, st);
+  return cudaErrorNotSupported;
 }
 
 template <int KL>
@@ -1037,8 +1112,16 @@ int default_shadow_kind(int row_elems) {
   return hilo_ok ? kShadowHiLo : (hi_ok ? kShadowHi : kShadowNone);
 }
 
+static bool filter_enabled() {
+  static const bool on = !(getenv("RAG_B200_F32_FILTER") && atoi(getenv("RAG_B200_F32_FILTER")) == 0);
+  return on;
+}
+
 int candidates_kept(int dtype, int k, int rerank, int shadow_kind) {
   if (dtype == 1 && !rerank) return k;
+  // hi-only filter, k <= 16: the top-k list itself stays in registers; the rows within 2 eps of it go to the
+  // per-thread buffers (Args::extra), not into a longer list
+  if (dtype != 1 && shadow_kind == kShadowHi && k <= 16 && filter_enabled()) return 16;
   // hi-only filter of an fp32 store: bf16 rounding moves a unit-norm dot product by ~1e-3 worst case, so the list
   // must reach that far beyond the k-th neighbour for the guard to certify it (1M x 384 unit-norm: ~rank 20-40)
   if (dtype != 1 && shadow_kind == kShadowHi) return k <= 32 ? 64 : (k <= 100 ? 128 : k + 64);
@@ -1146,6 +1229,14 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
     if (v <= 0) a.progress = nullptr;
     else if (v > 1) a.pace_window = static_cast<uint32_t>(v);
   }
+  const bool filt = hi_only && kk <= 16 && p.k <= 16 && filter_enabled() && (L.mode == 0 || L.mode == 2) && L.nb == kNB;
+  a.q_lo_norm2 = q_lo; a.x_max_norm2 = p.max_norm2; a.x_lo_max2 = p.lo_max2; a.guard_rel = kGuardRel;
+  a.extra = reinterpret_cast<uint64_t*>(p.scratch + L.off_extra);
+  a.extra_cnt = reinterpret_cast<int*>(p.scratch + L.off_extracnt);
+  if (filt && (p.max_norm2 == nullptr || p.lo_max2 == nullptr)) return cudaErrorInvalidValue;
+  // filter mode: the list only has to give the k-th best (the slack lives in the buffers), so it is k long, not kk
+  const int klist = filt ? p.k : kk;
+  a.k = klist;
   a.tau_q = nullptr;
   a.tau_q_rank = (kk + L.cpm - 1) / L.cpm;
   if (kk > 16 && L.cpm <= 32 && a.tau_q_rank <= 8 && !(getenv("RAG_B200_TENSOR_TAUQ") && atoi(getenv("RAG_B200_TENSOR_TAUQ")) == 0))
@@ -1154,18 +1245,21 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   if (e != cudaSuccess) return e;
   dim3 grid(L.cpm * L.cl, L.n_mtiles / L.cl, 1);
   const bool l2 = (p.space == 0);
-  if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.mode, L.nb, grid, st);
+  if (filt) e = launch_filter(tmap, a, l2, L.mode, grid, st);
+  else if (kk <= 16) e = launch_kl<16>(tmap, a, l2, L.mode, L.nb, grid, st);
   else if (kk <= 128) e = launch_kl<128>(tmap, a, l2, L.mode, L.nb, grid, st);
   else e = launch_kl<1024>(tmap, a, l2, L.mode, L.nb, grid, st);
   if (e != cudaSuccess) return e;
   out->partial = part;
   out->S = L.cpm;
-  out->k_kept = kk;
+  out->k_kept = klist;
   out->q_norm2 = q_norm;
   out->q_lo_norm2 = hi_only ? q_lo : nullptr;
   out->q_f32 = q_f32;
   out->q_exact = q_exact;
   out->merged = reinterpret_cast<uint64_t*>(p.scratch + L.off_merged);
+  out->filt = filt ? 1 : 0;
+  out->extra = a.extra; out->extra_cnt = a.extra_cnt; out->extra_cap = kFiltCap;
   if (launches) *launches += 2;
   return cudaSuccess;
 }

@@ -21,6 +21,8 @@ struct Problem {
   int shadow_kind;          // kernels.h: kShadowNone (bf16 stores), kShadowHi, kShadowHiLo
   const float* norms2;      // [n_rows] |x|^2 of the stored rows (l2 space)
   const float* min_norm2;   // [1] lower bound of norms2 over everything the store ever held
+  const float* max_norm2;   // [1] upper bound of the same   } error bound of the hi-only contraction
+  const float* lo_max2;     // [1] max |x - bf16(x)|^2        } (fp32 stores; kernels.h, UpsertArgs::lo_max2)
   int64_t n_rows;
   int row_elems, dim, dtype, space;
   const uint32_t* live;
@@ -55,6 +57,12 @@ struct Result {
   const float* q_f32;       // [B][row_elems] prepared queries (for the l2 refinement)
   const float* q_exact;     // [B][exact_elems] normalised, un-rounded queries (Problem::rerank)
   uint64_t* merged;         // [B][k_kept] scratch for the merged keys before refinement
+  // hi-only FILTER mode (fp32 store, kShadowHi, k <= 16): next to the approximate top-k lists every (CTA, query)
+  // left the rows within 2 eps of its bound; launch_refine_filter re-scores those within 2 eps of the merged k-th best
+  int filt;
+  const uint64_t* extra;    // [S][B][extra_cap]
+  const int* extra_cnt;     // [S][B], -1 = overflow
+  int extra_cap;
 };
 // epilogue selection counters (RAG_B200_TENSOR_STATS=1), see tensor_regime.cu
 int read_stats(unsigned long long* out8, int reset);
