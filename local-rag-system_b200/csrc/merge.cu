@@ -270,16 +270,16 @@ __global__ void __launch_bounds__(kMergeThreads) refine_filter_kernel(const Refi
   if (kth != kEmptyKey)
     thr = key_dist(kth) + 2.0f * bf16_contraction_eps(a.q_norm2[b], a.q_lo_norm2[b], a.x_max_norm2[0], a.x_lo_max2[0],
                                                        a.guard_rel, a.l2 != 0);
-  for (int idx = threadIdx.x; idx < fa.S * fa.cap; idx += blockDim.x) {
-    const int c = idx / fa.cap, i = idx - c * fa.cap;
+  for (int c = threadIdx.x; c < fa.S; c += blockDim.x) {      // one thread per CTA of the contraction: its few buffered rows
     const size_t slot = static_cast<size_t>(c) * a.B + b;
     const int cnt = fa.extra_cnt[slot];
-    if (cnt < 0) { if (i == 0) atomicExch(&s_over, 1); continue; }
-    if (i >= cnt) continue;
-    const uint64_t key = fa.extra[slot * fa.cap + i];
-    if (key_dist(key) <= thr) {
-      const int p = atomicAdd(&s_n, 1);
-      if (p < kFiltRefineCap) cand[p] = key; else atomicExch(&s_over, 1);
+    if (cnt < 0 || cnt > fa.cap) { atomicExch(&s_over, 1); continue; }
+    for (int i = 0; i < cnt; ++i) {
+      const uint64_t key = fa.extra[slot * fa.cap + i];
+      if (key_dist(key) <= thr) {
+        const int p = atomicAdd(&s_n, 1);
+        if (p < kFiltRefineCap) cand[p] = key; else atomicExch(&s_over, 1);
+      }
     }
   }
   __syncthreads();

@@ -1,6 +1,6 @@
 // K3 + K4: tensor-core search regime for large query batches.
 //
-// Replaces, for B > 2 queries (B > 6 on fp32 stores), the hnswlib graph walk / numpy brute force
+// Replaces, for B > 2 queries (B > 4 on fp32 stores), the hnswlib graph walk / numpy brute force
 // behind collection.query (api/app.py:544-549) with an exact dense contraction
 // Q[B x D] . X[N x D]^T on the 5th-generation tensor cores, with the top-k selection fused into
 // the epilogue so the B x N score matrix never exists.
@@ -291,6 +291,15 @@ struct Args {
   // same quantile as the global k-th best, cpm times tighter than any single CTA's own k-th best above.
   uint32_t* tau_q;
   int tau_q_rank;                // q (1..8)
+  // Group bound for k <= 16 (nullptr = off): [n_mtiles*128][grp_n] ordered(fp32), grp_n = min(cpm, k) groups of CTAs
+  // (cj % grp_n).  Every CTA keeps atomicMin-ing its own r-th best (r = grp_rank = ceil(k / grp_n)) into its group's
+  // slot: the CTA that set a slot holds r rows at or below it, the groups scan disjoint rows, so grp_n * r >= k rows
+  // lie at or below T = max over the slots and nothing beyond T can be in the global top-k.  T tracks the k-th best of
+  // everything ALL CTAs have seen -- `tau_shared` only the best single CTA's -- at grp_n <= 16 loads per refresh.
+  // It is what lets small corpora (a few thousand rows per CTA) leave the warm-up phase at all: 1M rows over 148
+  // CTAs had ~1 candidate per query and tile throughout, 7.6 k cycles of epilogue per 64-row tile.
+  uint32_t* tau_grp;
+  int grp_n, grp_rank;
   // [cpm][gridDim.y] inverted tile counters (0xFFFFFFFF - tiles issued) of the clusters that walk the same
   // corpus tiles for different query tiles.  A cluster may run at most kPaceWindow tiles ahead of its slowest
   // sibling, so a tile fetched from DRAM by the first cluster is still in L2 when the others ask for it
@@ -579,6 +588,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
                                              a.guard_rel, L2);
     }
 
+    const bool use_grp = (KL <= 16) && a.tau_grp != nullptr;
+    uint32_t* grp_row = use_grp ? a.tau_grp + static_cast<size_t>(mt * kM + m) * a.grp_n : nullptr;
+    uint32_t* grp_slot = use_grp ? grp_row + (cj % a.grp_n) : nullptr;
+    uint32_t grp_pub = 0xFFFFFFFFu;                  // what this thread last published to its group's slot
+
     uint32_t it = 0;
     TileWalker walk(a, cj, n_tiles);
     int64_t t;
@@ -587,14 +601,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
       ++it;
-      // every 8th tile: pick up the bound the sibling CTAs have published (the load overlaps the wait below)
-      const bool refresh = q_valid && ((it & 7u) == 1u);
+      // every 8th tile (and after the 1st, 2nd and 4th, while the bounds still move fast): pick up the bounds the
+      // sibling CTAs have published (the loads overlap the wait below)
+      const bool refresh = q_valid && ((it & 7u) == 1u || it == 2u || it == 3u || it == 5u);
       uint32_t tg_bits = 0xFFFFFFFFu;
-      if (refresh) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tg_bits) : "l"(tau_slot) : "memory");
+      uint32_t grp_worst = 0xFFFFFFFFu;
+      if (refresh) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tg_bits) : "l"(tau_slot) : "memory");
+        if constexpr (KL <= 16) {
+          if (use_grp) {
+            grp_worst = 0u;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              if (g < a.grp_n) {
+                uint32_t v;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(grp_row + g) : "memory");
+                grp_worst = v > grp_worst ? v : grp_worst;
+              }
+            }
+          }
+        }
+      }
       mbar_wait(accf_bar(buf), par);
       tc_fence_after();
       if (tg_bits != 0xFFFFFFFFu) {
         tau_g = fminf(tau_g, ordered_to_float(tg_bits));
+        tau = fminf(tau, tau_g);
+      }
+      if (grp_worst != 0xFFFFFFFFu) {                // every group has published: k rows lie at or below the largest slot
+        tau_g = fminf(tau_g, ordered_to_float(grp_worst));
         tau = fminf(tau, tau_g);
       }
       if constexpr (KL > 16) {
@@ -755,6 +790,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
             if (key < kth_key && dj <= tau_g) {
               if (a.stats) atomicAdd(&g_tensor_stats[4], 1ull);
               top.insert(key, k);
+              if constexpr (KL <= 16) {
+                if (use_grp) {                         // own r-th best -> the group's slot, when it has improved
+                  const uint64_t rk = top.kth(a.grp_rank);
+                  const uint32_t rv = static_cast<uint32_t>(rk >> 32);
+                  if (rk != kEmptyKey && rv < grp_pub) { atomicMin(grp_slot, rv); grp_pub = rv; }
+                }
+              }
               kth_key = top.kth(k);
               if (kth_key != kEmptyKey) {              // list is full: its k-th best bounds the global k-th best
                 const float own = key_dist(kth_key);
@@ -887,11 +929,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
     while (walk.next(t, wt)) {
       const int buf = it & (nbuf - 1);
       const uint32_t par = (it >> nbuf_log2) & 1;
-      // An issuer never looks at the full barriers of the other's tiles; with a ring of fewer than two whole tiles it
-      // can then get TWO phases ahead of a barrier (a stage whose next use belongs to the other issuer and has not
-      // even been loaded), where the parity test passes on stale data and the barriers receive arrivals out of phase
-      // (seen as launch failures with 4-5 stages at D = 768; a model of the protocol fails the same way for every
-      // ring shorter than 2 tiles and never for longer ones).  Short rings are therefore driven by ONE issuer.
+      // one issuer where the ring geometry does not let two issuers run without watching each other's stages
+      // (launch_one decides, with the reasons)
       const bool mine = a.one_issuer ? (issuer == 0u) : ((it & 1u) == issuer);
       ++it;
       if (!mine) {                                  // the other issuer's tile: step over its ring stages
@@ -1052,7 +1091,27 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
   }
   // the ring must hold at least one whole tile plus a stage, or producer and issuer wait for each other
   if (a.stages_used < per_tile + 1) a.stages_used = std::min(per_tile + 1, R::kStages);
-  a.one_issuer = (a.stages_used < 2 * per_tile) ? 1 : 0;
+  // Two MMA issuers take alternate tiles and never look at the full barriers of each other's stages.  An issuer about
+  // to poll a stage must therefore know, by other means, that the stage's PREVIOUS use has landed (TMA loads complete
+  // out of order) -- else its parity test passes on the phase before and everything derails (launch failures with
+  // 4-5 stages at D = 768; tools' protocol model fails the same way).  What an issuer of tile t does know: its own
+  // tile t-2 (it polled those stages) and every tile the epilogue has drained, i.e. up to t - nbuf (it waits for
+  // that accumulator).  With p stages per tile the previous use of a stage of tile t lies n_ring stages back, so:
+  //   n_ring == 2p            every stage always belongs to the same issuer                      -> safe
+  //   n_ring >= 2p, nbuf == 2 the previous use lies in tile t-2 or before                        -> safe
+  //   n_ring >= 4p            ... in tile t-4 or before                                          -> safe
+  //   2p < n_ring < 4p with 4 accumulators: it can lie in the OTHER issuer's tile t-3            -> clamp to 2p
+  //   n_ring < 2p             ... in the other issuer's tile t-1                                 -> one issuer
+  {
+    const int p2 = 2 * per_tile;
+    const int n = a.stages_used;
+    const bool safe_two = (n == p2) || (n >= p2 && a.nbuf == 2) || (n >= 2 * p2);
+    a.one_issuer = 0;
+    if (!safe_two) {
+      if (n > p2) a.stages_used = p2;
+      else a.one_issuer = 1;
+    }
+  }
   if (const char* ev = getenv("RAG_B200_TENSOR_ONE_ISSUER")) { if (atoi(ev) == 1) a.one_issuer = 1; }
   const int smem_bytes = a.stages_used * R::kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + list_bytes;
   if (smem_bytes > kSmemBytes) return cudaErrorInvalidConfiguration;
@@ -1106,10 +1165,10 @@ int default_shadow_kind(int row_elems) {
     if (!strcmp(e, "hilo") && hilo_ok) return kShadowHiLo;
     if (!strcmp(e, "hi") && hi_ok) return kShadowHi;
   }
-  // measured (1M x 384 fp32, B = 32 / 1024): hi/lo 0.44 / 1.90 ms; hi-only with 64-entry heaps 1.16 / 2.12 ms -- the
-  // per-thread heap insertions of the list warm-up cost more than the two MMAs saved -- so hi-only is what rows the
-  // split cannot take get (dim > 384 or dim % 16 != 0), until its selection is cheaper
-  return hilo_ok ? kShadowHiLo : (hi_ok ? kShadowHi : kShadowNone);
+  // measured (1M x 384 fp32, B = 32 / 1024, top-10): hi/lo split 0.36 / 1.87 ms, hi-only filter 0.28 / 1.15 ms.
+  // (k > 16 on a hi-only store keeps 64-128 candidates in per-thread heaps instead of the filter buffers, which is
+  // slower than the split; stores queried that way can be pinned with rag_store_set_f32_shadow.)
+  return hi_ok ? kShadowHi : (hilo_ok ? kShadowHiLo : kShadowNone);
 }
 
 static bool filter_enabled() {
@@ -1237,6 +1296,12 @@ cudaError_t launch(const Problem& p, cudaStream_t st, Result* out, int* launches
   // filter mode: the list only has to give the k-th best (the slack lives in the buffers), so it is k long, not kk
   const int klist = filt ? p.k : kk;
   a.k = klist;
+  a.tau_grp = nullptr; a.grp_n = 0; a.grp_rank = 0;
+  if (klist <= 16 && !(getenv("RAG_B200_TENSOR_GRP") && atoi(getenv("RAG_B200_TENSOR_GRP")) == 0)) {
+    a.grp_n = std::min(std::min(L.cpm, klist), 16);
+    a.grp_rank = (klist + a.grp_n - 1) / a.grp_n;
+    a.tau_grp = reinterpret_cast<uint32_t*>(p.scratch + L.off_tauq);      // the quantile bounds' block (k > 16 only): stride grp_n <= cpm
+  }
   a.tau_q = nullptr;
   a.tau_q_rank = (kk + L.cpm - 1) / L.cpm;
   if (kk > 16 && L.cpm <= 32 && a.tau_q_rank <= 8 && !(getenv("RAG_B200_TENSOR_TAUQ") && atoi(getenv("RAG_B200_TENSOR_TAUQ")) == 0))

@@ -11,9 +11,9 @@ namespace tensor {
 // tools/crossover.py (final round-1 kernels), 10M x 768 bf16: stream 2.07 / 2.24 / 3.09 ms at B = 1 / 2 / 3,
 // tensor 2.36-2.47 ms for any B <= 16
 constexpr int kStreamMaxBatch = 2;
-// fp32 stores (1M x 384): the exact stream kernel 0.21 / 0.27 / 0.38 / 0.41 ms at B = 1 / 4 / 6 / 8, the
-// split-precision contraction + exact re-ranking 0.35-0.40 ms for any B <= 16
-constexpr int kStreamMaxBatchF32 = 6;
+// fp32 stores (1M x 384): the exact stream kernel 0.21 / 0.27 / 0.38 / 0.41 ms at B = 1 / 4 / 6 / 8; the bf16-shadow
+// contraction + exact re-ranking 0.26-0.28 ms (hi-only filter) / 0.35 ms (hi/lo split) for any B <= 32
+constexpr int kStreamMaxBatchF32 = 4;
 
 struct Problem {
   const void* vectors;      // [n_rows][row_elems] bf16 (or fp32 when `shadow` is streamed instead), row-major

@@ -380,7 +380,7 @@ def test_auto_regime_switches_on_batch_size():
         assert st.last_query_info()["regime"] == "stream"
         st.query(x[:64], 5)
         assert st.last_query_info()["regime"] == "tensor"
-        f32.query(x[:6], 5)                                # fp32: up to 6 queries stay on the exact stream kernel
+        f32.query(x[:4], 5)                                # fp32: up to 4 queries stay on the exact stream kernel
         assert f32.last_query_info()["regime"] == "stream"
         f32.query(x[:64], 5)                               # beyond that: bf16-shadow contraction + exact re-rank
         assert f32.last_query_info()["regime"] == "tensor"
@@ -492,16 +492,17 @@ def test_fp32_hi_only_filter_certifies_spread_out_rows():
 
 
 def test_fp32_store_moves_to_split_precision_when_the_filter_cannot_certify():
-    """Rows packed far closer than bf16 can tell apart: the hi-only guard sends most queries to the exact
-    re-run (answers stay exact), the store notices and moves to the hi/lo split, which certifies them."""
-    n, dim, k, B = 6000, 256, 10, 96
+    """Rows packed far closer than bf16 can tell apart: more of them lie within the hi-only filter's error band
+    than it re-scores (512 per query), so it hands most queries to the exact re-run (answers stay exact); the
+    store notices and moves to the hi/lo split, whose band is 30 times narrower and certifies them."""
+    n, dim, k, B = 20000, 256, 10, 96
     rng = np.random.default_rng(9)
     centre = unit_rows(1, dim, 8)[0]
-    # cosine distances 0.1 +- 0.009: rank 10 and rank 64 of a query are ~5e-3 apart (the hi-only bound is 8e-3),
-    # rank 10 and rank 16 ~1e-3 (the split-precision bound is 2.4e-4) -- simulated in numpy when this was written
-    x = centre[None, :] + 2e-2 * rng.standard_normal((n, dim)).astype(np.float32)
+    # cosine distances 0.07 +- 0.006: 600-1500 rows within 2 eps = 8e-3 of a query's 10th neighbour, while ranks 10
+    # and 16 are ~1e-3 apart (the split-precision bound is 2.4e-4) -- simulated in numpy when this was written
+    x = centre[None, :] + 1.7e-2 * rng.standard_normal((n, dim)).astype(np.float32)
     x /= np.linalg.norm(x, axis=1, keepdims=True)
-    q = centre[None, :] + 2e-2 * rng.standard_normal((B, dim)).astype(np.float32)
+    q = centre[None, :] + 1.7e-2 * rng.standard_normal((B, dim)).astype(np.float32)
     st = DeviceStore(dim, "f32", "cosine")
     try:
         st.upsert(x)
@@ -539,7 +540,8 @@ def test_fp32_tensor_regime_near_ties_are_decided_exactly(shadow):
     x = unit_rows(n, dim, 31)
     rng = np.random.default_rng(32)
     base = x[100].copy()
-    cluster = np.arange(1000, 1000 + (60 if shadow == "hilo" else 200))      # more than the candidates either shadow keeps
+    # more near-identical rows than the hi/lo list's slack (16) / than the hi-only filter re-scores per query (512)
+    cluster = np.arange(1000, 1000 + (60 if shadow == "hilo" else 700))
     x[cluster] = base[None, :] + 2e-7 * rng.standard_normal((cluster.size, dim)).astype(np.float32)
     q = unit_rows(B, dim, 33)
     q[3] = base
