@@ -274,11 +274,16 @@ __global__ void __launch_bounds__(kMergeThreads) refine_filter_kernel(const Refi
     const size_t slot = static_cast<size_t>(c) * a.B + b;
     const int cnt = fa.extra_cnt[slot];
     if (cnt < 0 || cnt > fa.cap) { atomicExch(&s_over, 1); continue; }
-    for (int i = 0; i < cnt; ++i) {
-      const uint64_t key = fa.extra[slot * fa.cap + i];
-      if (key_dist(key) <= thr) {
-        const int p = atomicAdd(&s_n, 1);
-        if (p < kFiltRefineCap) cand[p] = key; else atomicExch(&s_over, 1);
+    for (int i0 = 0; i0 < cnt; i0 += 8) {           // 8 independent loads per round (a CTA leaves ~15-20 rows, few pass)
+      uint64_t kk[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) kk[u] = (i0 + u < cnt) ? __ldcg(fa.extra + slot * fa.cap + i0 + u) : kEmptyKey;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (kk[u] != kEmptyKey && key_dist(kk[u]) <= thr) {
+          const int p = atomicAdd(&s_n, 1);
+          if (p < kFiltRefineCap) cand[p] = kk[u]; else atomicExch(&s_over, 1);
+        }
       }
     }
   }

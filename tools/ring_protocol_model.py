@@ -1,3 +1,10 @@
+"""Model of the tensor regime's shared-memory ring protocol (tensor_regime.cu): one TMA producer, TWO MMA issuers on
+alternate tiles, mbarrier parity waits, nbuf accumulators drained in order by the epilogue.  Random interleaving of the
+agents; TMA loads may LAND OUT OF ORDER (30 % of the completions pick a random in-flight load).  Reports, per
+(ring stages, stages per tile, accumulators), whether an issuer ever passes a full-barrier wait on a stage that
+does not hold its tile's data -- the race behind the intermittent launch failures of short rings.
+With in-order landing (replace the random pick by j = 0) every geometry passes.
+    python tools/ring_protocol_model.py"""
 import random, sys
 def sim(n_ring, per_tile, n_tiles, nbuf, seed, epi_fast=True):
     rng = random.Random(seed)

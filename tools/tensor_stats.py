@@ -21,9 +21,10 @@ ap.add_argument("--space", default="l2")
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--rerank", type=int, default=1)
+ap.add_argument("--dtype", default="bf16")
 a = ap.parse_args()
 lib = _native.load()
-st = rag.DeviceStore(a.dim, "bf16", a.space, capacity_hint=a.rows, rerank=bool(a.rerank))
+st = rag.DeviceStore(a.dim, a.dtype, a.space, capacity_hint=a.rows, rerank=bool(a.rerank))
 gen = torch.Generator(device="cuda"); gen.manual_seed(1)
 for s in range(0, a.rows, 500_000):
     m = min(500_000, a.rows - s)
@@ -40,6 +41,6 @@ ms = st.last_query_info()["kernel_ms"]
 lib.rag_debug_tensor_stats(out, 1)
 v = list(out)
 tiles = max(v[0], 1)
-print(f"rows {a.rows} dim {a.dim} {a.space} k {a.k} B {a.batch} rerank {a.rerank}: kernel {ms:.2f} ms")
+print(f"rows {a.rows} dim {a.dim} {a.dtype} {a.space} k {a.k} B {a.batch} rerank {a.rerank}: kernel {ms:.3f} ms")
 print(f"  warp-tiles drained {v[0]}, passed reject #1 {v[1]} ({100 * v[1] / tiles:.1f} %), passed #2 {v[2]} ({100 * v[2] / tiles:.1f} %)")
 print(f"  candidate scores {v[3]} ({v[3] / tiles:.3f} per warp-tile), insertions {v[4]} ({v[4] / a.batch:.0f} per query), quantile updates {v[5]}")
