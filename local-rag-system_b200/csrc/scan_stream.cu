@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
   const int64_t nblk = (a.n_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   const int64_t wstride = static_cast<int64_t>(gridDim.x) * kScanWarps;
 
-  // One step of the scan: the R row slots `r[]` (row index relative to `base`, -1 = empty slot; with
+  // One step of the scan: the R row slots `r[]` (row index relative to `base` as an UNSIGNED 32-bit value, -1 =
+  // 0xFFFFFFFF = empty slot -- no store has that many rows; with
   // sub-warp rows each lane group carries its own row per slot) are loaded, contracted with the
   // queries and offered to the top-k lists.  `row0` = store row of `base`.
   auto process = [&](const uint4* base, int64_t row0, const int (&r)[R]) {
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       for (int i = 0; i < R; ++i) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          v[i][j] = (r[i] >= 0) ? ldg_stream(base + static_cast<size_t>(r[i]) * cpr + j * LPR + sl)
-                                : make_uint4(0u, 0u, 0u, 0u);
+          v[i][j] = (r[i] != -1) ? ldg_stream(base + static_cast<size_t>(static_cast<uint32_t>(r[i])) * cpr + j * LPR + sl)
+                                 : make_uint4(0u, 0u, 0u, 0u);
         }
       }
 #pragma unroll
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
         uint4 v[R];
 #pragma unroll
         for (int i = 0; i < R; ++i)
-          v[i] = (r[i] >= 0) ? ldg_stream(base + static_cast<size_t>(r[i]) * cpr + c) : make_uint4(0u, 0u, 0u, 0u);
+          v[i] = (r[i] != -1) ? ldg_stream(base + static_cast<size_t>(static_cast<uint32_t>(r[i])) * cpr + c) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int qb = 0; qb < QB; ++qb) {
           const float4* qrow = reinterpret_cast<const float4*>(q_s + qb * row_elems);
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
 #pragma unroll
     for (int i = 1; i < R; ++i) myr = (my_i == i) ? r[i] : myr;
     const float dist = L2 ? total : (1.0f - total);
-    const uint64_t key = make_key(dist, static_cast<uint32_t>(row0 + myr));
-    uint32_t bal = __ballot_sync(0xffffffffu, rep && (myr >= 0) && (key < my_tau));
+    const uint64_t key = make_key(dist, static_cast<uint32_t>(row0) + static_cast<uint32_t>(myr));
+    uint32_t bal = __ballot_sync(0xffffffffu, rep && (myr != -1) && (key < my_tau));
     while (bal) {
       const int src = __ffs(bal) - 1;
       bal &= (bal - 1);
@@ -292,7 +293,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
     // bits, and every step fills all R x G slots with the next passing rows of the chunk.
     constexpr int CW = 16;                              // bitmap words per chunk (512 rows)
     constexpr int kGatherMaxRows = CW * 32 / 4;         // gather when <= 25 % of the chunk's rows pass
-    __shared__ uint16_t s_pass[kScanWarps][kGatherMaxRows];   // per warp: offsets of the chunk's passing rows
+    // per warp: store rows that pass and have not been processed yet -- this chunk's and up to R*G - 1 carried
+    // over from earlier chunks: a step is only issued with all its slots filled (at 1 % selectivity a chunk holds
+    // ~5 passing rows for 8 slots; processing chunk by chunk left 40 % of the loads in flight empty and paid 8
+    // dependent steps per warp where 5 do)
+    constexpr int RG = R * G;
+    __shared__ uint32_t s_pass[kScanWarps][kGatherMaxRows + 32];
+    int fill = 0;                                       // rows waiting in the list (uniform across the warp)
     const int64_t nchunk = (nblk + CW - 1) / CW;
     auto fetch_words = [&](int64_t chunk) -> uint32_t {
       const int64_t w = chunk * CW + lane;
@@ -345,24 +352,38 @@ __global__ void __launch_bounds__(kScanThreads, 2) scan_stream_kernel(const Scan
       // ballot + shuffle + __fns: ~70 instructions per slot, 2/3 of the kernel's issue slots at 10 %.)
       {
         uint32_t m = word;
-        int pos = incl - pop;
+        int pos = fill + incl - pop;
+        const uint32_t row_of_word = static_cast<uint32_t>((chunk * CW + lane) * kRowsPerBlock);
         while (m) {
           const int bit = __ffs(m) - 1;
           m &= (m - 1);
-          s_pass[warp][pos++] = static_cast<uint16_t>(lane * kRowsPerBlock + bit);
+          s_pass[warp][pos++] = row_of_word + static_cast<uint32_t>(bit);
         }
       }
+      fill += T;
       __syncwarp();
-      for (int j0 = 0; j0 < T; j0 += R * G) {
+      int j0 = 0;
+      for (; j0 + RG <= fill; j0 += RG) {              // full steps only
         int r[R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const int j = j0 + i * G + grp;              // rank of the passing row that goes into this lane's slot i
-          r[i] = (j < T) ? static_cast<int>(s_pass[warp][j]) : -1;
-        }
-        process(cbase, chunk * (CW * kRowsPerBlock), r);
+        for (int i = 0; i < R; ++i) r[i] = static_cast<int>(s_pass[warp][j0 + i * G + grp]);   // rank -> this lane's slot i
+        process(vec, 0, r);
       }
-      __syncwarp();                                     // the list is rewritten for the next chunk
+      const int left = fill - j0;                       // < RG <= 16 rows stay for the next chunk: move them to the front
+      const uint32_t keep = (j0 > 0 && lane < left) ? s_pass[warp][j0 + lane] : 0u;
+      __syncwarp();
+      if (j0 > 0 && lane < left) s_pass[warp][lane] = keep;
+      fill = left;
+      __syncwarp();                                     // the list is appended to by the next chunk
+    }
+    if (fill > 0) {                                     // the last, partial step
+      int r[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int j = i * G + grp;
+        r[i] = (j < fill) ? static_cast<int>(s_pass[warp][j]) : -1;
+      }
+      process(vec, 0, r);
     }
   }
 

@@ -5,6 +5,8 @@ Bars (BASELINE.json north_star):
                ties within 1e-6; distances within 1e-5 relative + 1e-6 absolute.
   bf16 store : same inputs (the bf16-rounded vectors) -> recall@k >= 0.999.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -758,3 +760,16 @@ def test_tensor_regime_large_k_many_queries(space, k):
         check_against_oracle(space, "bf16", stored, q, k, rows, dists, counts, min_recall=0.999)
     finally:
         st.close()
+
+def test_short_shared_memory_rings_are_safe():
+    """Regression for the ring race of the tensor regime: with a ring shorter than two tiles the two
+    MMA issuers could run two barrier phases ahead of each other -- 10M x 768 never showed it (7 / 14 stages), a
+    4-stage ring failed with `unspecified launch failure` within a handful of batches.  Short rings are now driven
+    by one issuer; 300 batches with every launch synchronous must pass and keep returning the same rows."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1", STRESS_B="32", STRESS_DTYPE="bf16", RAG_B200_TENSOR_STAGES="4")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_f32.py"), "400000", "768", "hi", "300"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "300 batches ok" in r.stdout, (r.stdout[-600:], r.stderr[-1200:])
