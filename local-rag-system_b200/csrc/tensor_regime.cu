@@ -609,7 +609,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_topk_kernel(const __grid_con
       if (refresh) {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(tg_bits) : "l"(tau_slot) : "memory");
         if constexpr (KL <= 16) {
-          if (use_grp) {
+          // like the quantile bound of k > 16: every refresh while the bound still moves fast (the first q_early tiles
+          // of this CTA), every 128th tile afterwards -- refreshed every 8th tile throughout it cost the headline batch
+          // (10M x 768, B = 1024, 8.7 k tiles per CTA) 3-4 %: 13.5-13.9 -> 14.2 ms, same box
+          if (use_grp && (it < a.q_early || (it & a.q_late_mask) == 1u)) {
             grp_worst = 0u;
 #pragma unroll
             for (int g = 0; g < 16; ++g) {
