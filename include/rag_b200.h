@@ -282,6 +282,12 @@ RAG_API int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int*
  * CURRENT device, [0] tiles drained per warp, [1] / [2] tiles passing the first / second reject test,
  * [3] candidate scores examined, [4] list insertions, [5] quantile-list updates; out8 receives 8 counters */
 RAG_API int rag_debug_tensor_stats(uint64_t* out8, int reset);
+/* debugging aid, pure host logic (no device needed): the shared-memory ring the tensor-regime kernel runs with when
+ * `stages_available` stages fit, a corpus tile takes `stages_per_tile` of them and `accumulators` (2 or 4) buffers sit
+ * in tensor memory -- how many stages it uses and whether one warp issues every tile (tests/test_ring_protocol.py
+ * holds the answer to tools/ring_protocol_model.py) */
+RAG_API int rag_debug_ring_plan(int stages_available, int stages_per_tile, int accumulators, int* stages_used,
+                                int* one_issuer);
 /* device time (ms, CUDA events on the admin stream) of the upsert kernel of the last rag_store_upsert_dev */
 RAG_API float rag_store_last_upsert_ms(const rag_store* s);
 

@@ -98,6 +98,7 @@ SIGNATURES = {
     "rag_debug_tensor_stats": (C.c_int, [_u64p, C.c_int]),
     "rag_store_last_upsert_ms": (C.c_float, [_p]),
     "rag_store_last_query_info": (C.c_int, [_p, _f32p, _i32p, _i32p]),
+    "rag_debug_ring_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, _i32p, _i32p]),
     "rag_store_set_f32_shadow": (C.c_int, [_p, C.c_int]),
     "rag_store_f32_tensor_info": (C.c_int, [_p, _i32p, _i64p, _i64p]),
 }

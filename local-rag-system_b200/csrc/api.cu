@@ -1677,6 +1677,14 @@ int rag_store_set_f32_shadow(rag_store* s, int kind) {
   return flush_if_pending(s);
 }
 
+int rag_debug_ring_plan(int stages_available, int stages_per_tile, int accumulators, int* stages_used, int* one_issuer) {
+  if (!stages_used || !one_issuer || stages_per_tile < 1 || stages_available < stages_per_tile + 1 ||
+      (accumulators != 2 && accumulators != 4))
+    return fail(RAG_EINVAL, "bad ring geometry");
+  tensor::plan_ring(stages_available, stages_per_tile, accumulators, stages_used, one_issuer);
+  return RAG_OK;
+}
+
 int rag_store_last_query_info(const rag_store* s, float* kernel_ms, int* regime, int* launches) {
   if (!s) return fail(RAG_EINVAL, "store is NULL");
   rag_store* ms_ = const_cast<rag_store*>(s);

@@ -1094,27 +1094,7 @@ cudaError_t launch_one(const CUtensorMap& tmap, Args a, dim3 grid, cudaStream_t 
   }
   // the ring must hold at least one whole tile plus a stage, or producer and issuer wait for each other
   if (a.stages_used < per_tile + 1) a.stages_used = std::min(per_tile + 1, R::kStages);
-  // Two MMA issuers take alternate tiles and never look at the full barriers of each other's stages.  An issuer about
-  // to poll a stage must therefore know, by other means, that the stage's PREVIOUS use has landed (TMA loads complete
-  // out of order) -- else its parity test passes on the phase before and everything derails (launch failures with
-  // 4-5 stages at D = 768; tools' protocol model fails the same way).  What an issuer of tile t does know: its own
-  // tile t-2 (it polled those stages) and every tile the epilogue has drained, i.e. up to t - nbuf (it waits for
-  // that accumulator).  With p stages per tile the previous use of a stage of tile t lies n_ring stages back, so:
-  //   n_ring == 2p            every stage always belongs to the same issuer                      -> safe
-  //   n_ring >= 2p, nbuf == 2 the previous use lies in tile t-2 or before                        -> safe
-  //   n_ring >= 4p            ... in tile t-4 or before                                          -> safe
-  //   2p < n_ring < 4p with 4 accumulators: it can lie in the OTHER issuer's tile t-3            -> clamp to 2p
-  //   n_ring < 2p             ... in the other issuer's tile t-1                                 -> one issuer
-  {
-    const int p2 = 2 * per_tile;
-    const int n = a.stages_used;
-    const bool safe_two = (n == p2) || (n >= p2 && a.nbuf == 2) || (n >= 2 * p2);
-    a.one_issuer = 0;
-    if (!safe_two) {
-      if (n > p2) a.stages_used = p2;
-      else a.one_issuer = 1;
-    }
-  }
+  plan_ring(a.stages_used, per_tile, a.nbuf, &a.stages_used, &a.one_issuer);
   if (const char* ev = getenv("RAG_B200_TENSOR_ONE_ISSUER")) { if (atoi(ev) == 1) a.one_issuer = 1; }
   const int smem_bytes = a.stages_used * R::kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + list_bytes;
   if (smem_bytes > kSmemBytes) return cudaErrorInvalidConfiguration;
@@ -1155,6 +1135,31 @@ cudaError_t launch_kl(const CUtensorMap& tmap, const Args& a, bool l2, int mode,
 }
 
 }  // namespace
+
+// Ring stages the kernel may use with `avail` stages of shared memory, p = per_tile stages per corpus tile and nbuf
+// accumulators, and whether ONE warp has to issue every tile.
+// Two MMA issuers take alternate tiles and never look at the full barriers of each other's stages.  An issuer about
+// to poll a stage must therefore know, by other means, that the stage's PREVIOUS use has landed (TMA loads complete
+// out of order) -- else its parity test passes on the phase before and everything derails (launch failures with
+// 4-5 stages at D = 768; tools/ring_protocol_model.py fails the same way; tests/test_ring_protocol.py holds this
+// function to that model).  What an issuer of tile t does know: its own tile t-2 (it polled those stages) and
+// every tile the epilogue has drained, i.e. up to t - nbuf (it waits for that accumulator).  The previous use of a
+// stage of tile t lies n stages back, so:
+//   n == 2p            every stage always belongs to the same issuer                      -> safe
+//   n >= 2p, nbuf == 2 the previous use lies in tile t-2 or before                        -> safe
+//   n >= 4p            ... in tile t-4 or before                                          -> safe
+//   2p < n < 4p with 4 accumulators: it can lie in the OTHER issuer's tile t-3            -> clamp to 2p
+//   n < 2p             ... in the other issuer's tile t-1                                 -> one issuer
+void plan_ring(int avail, int per_tile, int nbuf, int* stages, int* one_issuer) {
+  const int p2 = 2 * per_tile;
+  const bool safe_two = (avail == p2) || (avail >= p2 && nbuf == 2) || (avail >= 2 * p2);
+  *stages = avail;
+  *one_issuer = 0;
+  if (!safe_two) {
+    if (avail > p2) *stages = p2;
+    else *one_issuer = 1;
+  }
+}
 
 static bool split_enabled() {
   static const bool on = !(getenv("RAG_B200_F32_TENSOR") && atoi(getenv("RAG_B200_F32_TENSOR")) == 0);

@@ -64,6 +64,8 @@ struct Result {
   const int* extra_cnt;     // [S][B], -1 = overflow
   int extra_cap;
 };
+// shared-memory ring the kernel runs with (host logic; tensor_regime.cu has the reasoning)
+void plan_ring(int avail, int per_tile, int nbuf, int* stages, int* one_issuer);
 // epilogue selection counters (RAG_B200_TENSOR_STATS=1), see tensor_regime.cu
 int read_stats(unsigned long long* out8, int reset);
 // Runs prep + contraction + fused select.
