@@ -20,11 +20,15 @@
 //     query, 64 scores), hand the buffer back, reject the whole tile with a 32-instruction
 //     three-input-max test against a bound shared by all CTAs of the query tile, and only otherwise
 //     walk the scores and insert survivors into a per-thread list (registers for k <= 16, a max-heap
-//     in local memory beyond).  live/filter bitmaps are applied on the survivor path; tiles whose 64
-//     rows are all dead or filtered are skipped by every role.
-//   * fp32 stores are contracted as bf16 hi/lo pairs (3 MMAs per k-step) and re-ranked exactly.
+//     in shared memory up to k = 128, in local memory beyond).  live/filter bitmaps are applied on the
+//     survivor path; tiles whose 64 rows are all dead or filtered are skipped by every role.
+//   * the bound: the thread's own k-th best, the best k-th best of the sibling CTAs of the query
+//     tile, and a bound built from ALL of them (k <= 16: group bound; larger k: quantile bound).
+//   * fp32 stores are contracted through a bf16 shadow of their rows -- bf16(x) alone (FILT: every row
+//     within the rounding bound of the running k-th best is buffered and re-scored exactly afterwards)
+//     or hi/lo pairs (3 MMAs per k-step, k + slack candidates re-ranked + an a-posteriori guard).
 //   * warp roles: 0 = TMA producer, 1 and 6 = MMA issuers on alternate tiles (1 owns the TMEM
-//     allocation), 2-5 = epilogue.
+//     allocation; ONE issuer where plan_ring() says the ring is too short for two), 2-5 = epilogue.
 //
 // Roofline: HBM for B <= ~256 (corpus read once), tensor pipe beyond.  Algorithmic FLOPs = 2 B N D.
 #include "tensor_regime.h"
