@@ -558,6 +558,11 @@ int rag::search_device(rag_store* s, QueryCtx* c, unsigned char* scratch, int B,
   int launches = 0;
   int S = 0;
   tensor::Result tres{};
+  // (a multi-shard front end decides the regime on ONE shard; another shard's shadow may have moved to a kind that
+  // cannot take this k: answer exactly on the stream kernel rather than fail)
+  if (regime == 2 && !forced_tensor &&
+      !tensor::supported(s->dtype, s->row_elems, k, s->space, s->exact_elems ? 1 : 0, s->shadow_kind))
+    regime = 1;
   if (regime == 2 && s->dtype == RAG_DTYPE_F32) {
     // the tensor regime contracts a bf16 shadow of the rows (half as many bytes again, or as many for the hi/lo
     // split).  If the device cannot hold it, an AUTO query is still answered -- exactly, by the stream kernel.
