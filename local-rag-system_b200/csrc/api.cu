@@ -500,7 +500,11 @@ int rag::choose_regime(const rag_store* s, int B, int k, int flags) {
   if (!tensor_ok) return 1;
   // the stream kernel reads the corpus once per group of <= 8 queries; the tensor kernel
   // once per 128 (HBM-bound up to ~256 queries, tensor-bound beyond)
-  if (s->dtype == RAG_DTYPE_F32) return (B > tensor::kStreamMaxBatchF32) ? 2 : 1;
+  if (s->dtype == RAG_DTYPE_F32) {
+    if (B > tensor::kStreamMaxBatchF32) return 2;
+    const bool big = (size_t)s->rows * s->row_bytes >= tensor::kF32TensorAlwaysBytes;
+    return (big && k <= 16 && s->shadow_kind == kShadowHi) ? 2 : 1;       // half the bytes per query (tensor_regime.h)
+  }
   return (B > tensor::kStreamMaxBatch) ? 2 : 1;
 }
 

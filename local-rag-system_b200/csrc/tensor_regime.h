@@ -14,6 +14,11 @@ constexpr int kStreamMaxBatch = 2;
 // fp32 stores (1M x 384): the exact stream kernel 0.21 / 0.27 / 0.38 / 0.41 ms at B = 1 / 4 / 6 / 8; the bf16-shadow
 // contraction + exact re-ranking 0.26-0.28 ms (hi-only filter) / 0.35 ms (hi/lo split) for any B <= 32
 constexpr int kStreamMaxBatchF32 = 4;
+// ... and ANY batch, down to a single query, once an fp32 store with the hi-only shadow (top-k <= 16: the filter path)
+// holds this many bytes of rows: the shadow is half the bytes of the fp32 rows the stream kernel reads, which beats
+// the fixed cost of the tensor regime's five launches (tools/crossover.py, B = 1: 1M x 384 0.198 vs 0.215 ms,
+// 1M x 768 0.323 vs 0.423 ms; the reference's own 25-vector collection stays on the one-launch stream kernel)
+constexpr size_t kF32TensorAlwaysBytes = (size_t)1 << 30;
 
 struct Problem {
   const void* vectors;      // [n_rows][row_elems] bf16 (or fp32 when `shadow` is streamed instead), row-major

@@ -386,6 +386,20 @@ def test_auto_regime_switches_on_batch_size():
         assert f32.last_query_info()["regime"] == "stream"
         f32.query(x[:64], 5)                               # beyond that: bf16-shadow contraction + exact re-rank
         assert f32.last_query_info()["regime"] == "tensor"
+        big = DeviceStore(256, "f32", "cosine", capacity_hint=1_100_000)     # >= 1 GiB of fp32 rows: the half-size
+        try:                                                                  # shadow wins even for a single query
+            rng = np.random.default_rng(7)
+            for _ in range(11):
+                big.upsert(rng.standard_normal((100_000, 256), dtype=np.float32))
+            q1 = rng.standard_normal((3, 256), dtype=np.float32)
+            r_t, d_t, _ = big.query(q1[:1], 10)
+            assert big.last_query_info()["regime"] == "tensor" and big.f32_tensor_info()["shadow"] == "hi"
+            r_s, d_s, _ = big.query(q1[:1], 10, regime="stream")
+            assert np.array_equal(r_t, r_s) and np.allclose(d_t, d_s, rtol=1e-5, atol=2e-6)
+            big.query(q1, 100)                             # k > 16 is not the filter path: small batches stay on the stream kernel
+            assert big.last_query_info()["regime"] == "stream"
+        finally:
+            big.close()
         odd = DeviceStore(100, "f32", "cosine")            # no shadow fits (row pitch % 8 != 0): stays on the stream kernel
         try:
             odd.upsert(unit_rows(500, 100, 2))
