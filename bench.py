@@ -24,7 +24,9 @@ One JSON line on rank 0 (keys per the driver contract):
             recall_bf16_vs_fp32 = recall@k of the bf16 store against exact fp32 search on the
             un-rounded inputs, >= 1000 queries
   regimes   the other BASELINE configs on the same box: B = 1024 on the headline corpus, config 2
-            (1M x 384 fp32, B = 1 / 32 / 1024), config 4 (10M x 384, `where` at 1 / 10 / 50 % with 5 %
+            (1M x 384 fp32, B = 1 / 32 / 1024, with `f32_tensor`: the bf16 shadow in force and how many
+            queries had to be re-run exactly; plus 1M x 768 fp32, labelled as beyond BASELINE), config 4
+            (10M x 384, `where` at 1 / 10 / 50 % with 5 %
             tombstones), config 5's per-GPU shard (25M x 384, B = 1024, top-100, l2); each with its
             own roofline
   cpu_baseline  the oracle's BLAS exact search on a bounded sample (N = 1 only)
