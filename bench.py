@@ -807,7 +807,9 @@ def main():
     if regime_seen == "tensor":
         kernel_ms = total_ms / K
         timing = "the timed region (the contraction is > 99.8 % of a step)"
-    roof = roofline_of(pk, regime_seen, B, n_local, args.dim, args.dtype, kernel_ms, live_frac, 1 if mask_slot >= 0 else 0)
+    shadow = store.f32_tensor_info()["shadow"] if (args.dtype == "f32" and regime_seen == "tensor") else None
+    roof = roofline_of(pk, regime_seen, B, n_local, args.dim, args.dtype, kernel_ms, live_frac, 1 if mask_slot >= 0 else 0,
+                       shadow=shadow)
     roof["timing"] = timing
     attach_traffic(roof, n_local, args.dim, args.dtype, B, args.selectivity or None)
 
