@@ -18,8 +18,13 @@ def parity_wait(completed_phases: int, parity: int) -> bool:
     return (completed_phases & 1) != parity
 
 
-def sim(n_ring: int, per_tile: int, n_tiles: int, nbuf: int, seed: int, one_issuer: bool = False, ooo: float = 0.3) -> str:
+def sim(n_ring: int, per_tile: int, n_tiles: int, nbuf: int, seed: int, one_issuer: bool = False, ooo: float = 0.3,
+        straggler: bool = False) -> str:
+    """straggler: now and then ONE in-flight load is held back for as long as anything else can make progress -- the
+    worst case of out-of-order landing (a DRAM straggler), which random interleaving alone rarely produces."""
     rng = random.Random(seed)
+    held = None                    # the in-flight load currently held back
+    idle = 0                       # consecutive steps in which no agent made progress
     full_c = [0] * n_ring          # completed phases of the full / empty barrier of every stage
     empty_c = [0] * n_ring
     content = [None] * n_ring      # (tile, k-stage) the stage holds
@@ -32,11 +37,35 @@ def sim(n_ring: int, per_tile: int, n_tiles: int, nbuf: int, seed: int, one_issu
     mma_queue = []                 # MMAs issued, not retired: (issuer, what their commit signals, argument)
     epi_it = 0
     steps = 0
+    sig = None
     while epi_it < n_tiles:
+        now = (prod["t"], prod["ks"], len(in_flight), issuers[0]["it"], issuers[0]["ks"], issuers[0]["state"],
+               issuers[1]["it"], issuers[1]["ks"], issuers[1]["state"], len(mma_queue), epi_it)
+        if now != sig:
+            idle = 0
+            sig = now
         steps += 1
         if steps > 3_000_000:
             return "deadlock"
         agent = rng.choice(("prod", "tma", "i0", "i1", "mma", "epi"))
+        idle += 1
+        if straggler and held is None and in_flight and rng.random() < 0.002:
+            held = rng.choice(in_flight)
+        if agent == "tma" and held is not None:
+            others = [x for x in in_flight if x is not held]
+            if others:
+                s, tag = others[rng.randrange(len(others)) if rng.random() < ooo else 0]
+                in_flight.remove((s, tag))
+                content[s] = tag
+                full_c[s] += 1
+                idle = 0
+            elif idle > 400:       # nothing else has moved for a long time: the straggler finally lands
+                in_flight.remove(held)
+                content[held[0]] = held[1]
+                full_c[held[0]] += 1
+                held = None
+                idle = 0
+            continue
         if agent == "prod" and prod["t"] < n_tiles:
             s = prod["s"]
             if parity_wait(empty_c[s], prod["ph"] ^ 1):
@@ -111,15 +140,15 @@ def sim(n_ring: int, per_tile: int, n_tiles: int, nbuf: int, seed: int, one_issu
     return "ok"
 
 
-def outcomes(n_ring, per_tile, nbuf, one_issuer=False, seeds=200, tiles=60, ooo=0.3):
-    return {sim(n_ring, per_tile, tiles, nbuf, seed, one_issuer, ooo)[:40] for seed in range(seeds)}
+def outcomes(n_ring, per_tile, nbuf, one_issuer=False, seeds=200, tiles=60, ooo=0.3, straggler=False):
+    return {sim(n_ring, per_tile, tiles, nbuf, seed, one_issuer, ooo, straggler)[:40] for seed in range(seeds)}
 
 
 if __name__ == "__main__":
     for nbuf in (2, 4):
         for per_tile in (2, 3):
             for n_ring in range(per_tile + 1, 15):
-                two = outcomes(n_ring, per_tile, nbuf)
-                one = outcomes(n_ring, per_tile, nbuf, one_issuer=True, seeds=50)
+                two = outcomes(n_ring, per_tile, nbuf) | outcomes(n_ring, per_tile, nbuf, straggler=True)
+                one = outcomes(n_ring, per_tile, nbuf, one_issuer=True, seeds=50) | outcomes(n_ring, per_tile, nbuf, one_issuer=True, seeds=50, straggler=True)
                 print(f"stages {n_ring:2d}  per tile {per_tile}  accumulators {nbuf}:  two issuers "
                       f"{'ok' if two == {'ok'} else 'RACE'}   one issuer {'ok' if one == {'ok'} else 'RACE'}")
