@@ -80,3 +80,34 @@ def test_rows_within_two_eps_of_the_approximate_kth_best_contain_the_exact_top_k
         assert needed <= candidates, (b, sorted(needed - candidates))
         sizes.append(len(candidates))
     assert min(sizes) >= k and np.median(sizes) < n / 4                         # a filter, not the whole corpus
+
+
+@pytest.mark.parametrize("cpm,k", [(148, 10), (18, 10), (18, 16), (9, 16), (4, 10), (1, 7), (37, 1), (74, 16)])
+def test_group_bound_never_undercuts_the_global_kth_best(cpm, k):
+    """tensor_regime.cu, Args::tau_grp: min(cpm, k) groups of CTAs (cj % groups); every CTA atomicMin-s its own r-th
+    best, r = ceil(k / groups), into its group's slot; T = the largest slot.  At ANY moment of the scan -- every
+    CTA having seen an arbitrary prefix of its rows -- T must be at or above the k-th best of all rows (else rows of
+    the true top-k would be rejected), and once everything is scanned it should be close to it."""
+    rng = np.random.default_rng(cpm * 100 + k)
+    groups = min(cpm, k, 16)
+    r = -(-k // groups)
+    assert groups * r >= k
+    for trial in range(20):
+        rows_per_cta = rng.integers(r, 400, size=cpm)
+        d = [rng.standard_normal(n) for n in rows_per_cta]                  # distances of each CTA's rows, in scan order
+        kth_global = np.sort(np.concatenate(d))[k - 1]
+        for frac in (0.05, 0.3, 0.7, 1.0):
+            slots = np.full(groups, np.inf)
+            for cj in range(cpm):
+                seen = d[cj][: max(int(len(d[cj]) * rng.uniform(frac * 0.5, frac) + 0.999), 0)]
+                if len(seen) >= r:                                          # a CTA publishes once its list holds r rows
+                    slots[cj % groups] = min(slots[cj % groups], np.sort(seen)[r - 1])
+            T = slots.max()                                                 # +inf until every group has published
+            assert T >= kth_global
+    # ... and it is a useful bound: with every CTA done (300 rows each) it sits within a small multiple of k ranks
+    d = [rng.standard_normal(300) for _ in range(cpm)]
+    slots = np.full(groups, np.inf)
+    for cj in range(cpm):
+        slots[cj % groups] = min(slots[cj % groups], np.sort(d[cj])[r - 1])
+    rank_of_T = int(np.sum(np.concatenate(d) <= slots.max()))
+    assert k <= rank_of_T <= 8 * k * (1 + np.log(k)) + 8 * r + 8, rank_of_T
